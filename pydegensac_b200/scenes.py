@@ -1,0 +1,75 @@
+"""Synthetic two-view scenes used by the benchmark and the parity tests.
+
+These reproduce the configurations BASELINE.json names; they are data generators only.
+"""
+import numpy as np
+
+_K = np.array([[800.0, 0.0, 320.0], [0.0, 800.0, 240.0], [0.0, 0.0, 1.0]])
+
+
+def _rot(ax, a):
+    c, s = np.cos(a), np.sin(a)
+    if ax == "x":
+        return np.array([[1, 0, 0], [0, c, -s], [0, s, c]], dtype=np.float64)
+    if ax == "y":
+        return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], dtype=np.float64)
+    return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], dtype=np.float64)
+
+
+def scene_F(n=2000, inlier_ratio=0.30, seed=0, plane_frac=0.0, noise=0.3):
+    """Scene F(N, rho, seed, pi): two pinhole views of random 3-D points + uniform outliers.
+
+    Returns (pts1 [N,2], pts2 [N,2], is_inlier [N]) float64; inliers first, then outliers.
+    """
+    rng = np.random.default_rng(seed)
+    n_in = int(n * inlier_ratio)
+    X = np.empty((n_in, 3))
+    X[:, 0] = rng.uniform(-2, 2, n_in)
+    X[:, 1] = rng.uniform(-2, 2, n_in)
+    X[:, 2] = rng.uniform(4, 10, n_in)
+    n_pl = int(n_in * plane_frac)
+    if n_pl > 0:
+        X[:n_pl, 2] = 6.0 + 0.1 * X[:n_pl, 0]
+    R = _rot("z", 0.03) @ _rot("y", -0.2) @ _rot("x", 0.05)
+    t = np.array([1.0, 0.1, 0.2])
+    x1 = (_K @ X.T).T
+    x2 = (_K @ (R @ X.T + t[:, None])).T
+    p1 = x1[:, :2] / x1[:, 2:3] + rng.normal(0, noise, (n_in, 2))
+    p2 = x2[:, :2] / x2[:, 2:3] + rng.normal(0, noise, (n_in, 2))
+    n_out = n - n_in
+    o1 = np.stack([rng.uniform(0, 640, n_out), rng.uniform(0, 480, n_out)], 1)
+    o2 = np.stack([rng.uniform(0, 640, n_out), rng.uniform(0, 480, n_out)], 1)
+    pts1 = np.concatenate([p1, o1], 0)
+    pts2 = np.concatenate([p2, o2], 0)
+    gt = np.zeros(n, dtype=bool)
+    gt[:n_in] = True
+    return np.ascontiguousarray(pts1), np.ascontiguousarray(pts2), gt
+
+
+H_GT = np.array([[1.1, 0.05, 10.0], [-0.03, 0.95, -5.0], [1e-4, -5e-5, 1.0]])
+
+
+def scene_H(n=5000, n_in=1500, seed=0, noise=0.5):
+    """H scene of BASELINE config 3: b = proj(H_GT a) + N(0, noise) on inliers, uniform outliers."""
+    rng = np.random.default_rng(seed)
+    a = np.stack([rng.uniform(0, 640, n_in), rng.uniform(0, 640, n_in)], 1)
+    ah = np.concatenate([a, np.ones((n_in, 1))], 1) @ H_GT.T
+    b = ah[:, :2] / ah[:, 2:3] + rng.normal(0, noise, (n_in, 2))
+    n_out = n - n_in
+    o1 = np.stack([rng.uniform(0, 640, n_out), rng.uniform(0, 640, n_out)], 1)
+    o2 = np.stack([rng.uniform(0, 640, n_out), rng.uniform(0, 640, n_out)], 1)
+    pts1 = np.concatenate([a, o1], 0)
+    pts2 = np.concatenate([b, o2], 0)
+    gt = np.zeros(n, dtype=bool)
+    gt[:n_in] = True
+    return np.ascontiguousarray(pts1), np.ascontiguousarray(pts2), gt
+
+
+def batch_F(n_pairs, n=2000, inlier_ratio=0.30, seed0=0, plane_frac=0.0):
+    """Config 5: n_pairs scenes F(n, rho, seed=s) for s = seed0 .. seed0+n_pairs-1, stacked [P,N,2]."""
+    p1 = np.empty((n_pairs, n, 2))
+    p2 = np.empty((n_pairs, n, 2))
+    for s in range(n_pairs):
+        a, b, _ = scene_F(n, inlier_ratio, seed0 + s, plane_frac)
+        p1[s], p2[s] = a, b
+    return p1, p2
