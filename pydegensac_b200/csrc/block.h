@@ -1,0 +1,148 @@
+// block.h -- CTA-cooperative primitives for the per-pair engine: deterministic block reductions,
+// ordered inlier compaction (the reference's `inlidxs`, rtools.c:160-171, done by a block scan) and
+// the execution context.  One CTA owns one image pair; every thread runs the same scalar control
+// flow on identical values (block reductions broadcast their result), so RANSAC state is replicated
+// in registers and only tiny solves are single-threaded.
+#pragma once
+#include "common.h"
+#include "la.h"
+
+namespace dg {
+
+constexpr int kMaxWarps = 16;      // CTA size <= 512
+constexpr int kVecRed = 48;        // widest vector reduction (45 covariance entries)
+
+struct BlockScratch {
+  double red_d[kMaxWarps];
+  int red_i[kMaxWarps];
+  double vec[kMaxWarps * kVecRed];
+  double vec_out[kVecRed];
+  double bc[32];                   // broadcast area for small results (models, scalars)
+  int bci[16];
+  int counter[4];                  // atomic counters of the hypothesis wave
+};
+
+struct Ctx {
+  int tid, nt, lane, wid, nw;
+  int N;
+  const double* x1; const double* y1; const double* x2; const double* y2;   // SoA correspondences
+  BlockScratch* sc;
+};
+
+#if DG_DEVICE_PASS
+DG_ENG inline double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+DG_ENG inline int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+DG_ENG inline int warp_incl_scan_i(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+DG_ENG inline int atomic_inc_shared(int* p) { return atomicAdd(p, 1); }
+#else
+inline double warp_sum(double v) { return v; }
+inline int warp_sum_i(int v) { return v; }
+inline int warp_incl_scan_i(int v, int) { return v; }
+inline int atomic_inc_shared(int* p) { return (*p)++; }
+#endif
+
+// Sum over the CTA, same value returned to every thread, fixed combination order.
+DG_ENG inline double blk_sum(const Ctx& c, double v) {
+  v = warp_sum(v);
+  DG_SYNC();
+  if (c.lane == 0) c.sc->red_d[c.wid] = v;
+  DG_SYNC();
+  double s = 0.0;
+  for (int w = 0; w < c.nw; ++w) s += c.sc->red_d[w];
+  return s;
+}
+DG_ENG inline int blk_sum_i(const Ctx& c, int v) {
+  v = warp_sum_i(v);
+  DG_SYNC();
+  if (c.lane == 0) c.sc->red_i[c.wid] = v;
+  DG_SYNC();
+  int s = 0;
+  for (int w = 0; w < c.nw; ++w) s += c.sc->red_i[w];
+  return s;
+}
+// Exclusive prefix over threads (thread order) + total.
+DG_ENG inline int blk_excl_scan_i(const Ctx& c, int v, int* total) {
+  const int incl = warp_incl_scan_i(v, c.lane);
+  DG_SYNC();
+  if (c.lane == 31 || c.tid == c.nt - 1) c.sc->red_i[c.wid] = incl;
+  DG_SYNC();
+  int base = 0, tot = 0;
+  for (int w = 0; w < c.nw; ++w) {
+    const int t = c.sc->red_i[w];
+    if (w < c.wid) base += t;
+    tot += t;
+  }
+  *total = tot;
+  return base + incl - v;
+}
+// k-wide vector sum (k <= kVecRed); result in c.sc->vec_out[0..k), visible to all threads on return.
+DG_ENG inline void blk_sum_vec(const Ctx& c, double* v, int k) {
+  DG_SYNC();
+  for (int i = 0; i < k; ++i) {
+    const double s = warp_sum(v[i]);
+    if (c.lane == 0) c.sc->vec[c.wid * kVecRed + i] = s;
+  }
+  DG_SYNC();
+  for (int i = c.tid; i < k; i += c.nt) {
+    double s = 0.0;
+    for (int w = 0; w < c.nw; ++w) s += c.sc->vec[w * kVecRed + i];
+    c.sc->vec_out[i] = s;
+  }
+  DG_SYNC();
+}
+// Broadcast n doubles computed by thread 0 (already stored in c.sc->bc) to every thread's `dst`.
+DG_ENG inline void bc_fetch(const Ctx& c, double* dst, int n) {
+  DG_SYNC();
+  for (int i = 0; i < n; ++i) dst[i] = c.sc->bc[i];
+  DG_SYNC();
+}
+
+// MSAC score + ascending inlier index list of a residual row (reference inlidxs, rtools.c:160-171):
+// J = sum truncQuad(err, th), list = {i : err[i] <= th}.  Threads own contiguous index segments so the
+// list comes out ordered after one block scan.
+DG_ENG inline Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list) {
+  const int per = (c.N + c.nt - 1) / c.nt;
+  const int beg = c.tid * per;
+  const int end = (beg + per < c.N) ? beg + per : c.N;
+  int cnt = 0;
+  double J = 0.0;
+  for (int i = beg; i < end; ++i) {
+    const double e = err[i];
+    J += trunc_quad(e, th);
+    if (e <= th) ++cnt;
+  }
+  int total;
+  int off = blk_excl_scan_i(c, cnt, &total);
+  for (int i = beg; i < end; ++i)
+    if (err[i] <= th) list[off++] = i;
+  Score s = make_score();
+  s.J = blk_sum(c, J);
+  s.I = (unsigned)total;
+  DG_SYNC();
+  return s;
+}
+
+// count of err[i] < th (strict) or <= th over all points
+DG_ENG inline int blk_count_lt(const Ctx& c, const double* err, double th) {
+  int cnt = 0;
+  for (int i = c.tid; i < c.N; i += c.nt)
+    if (err[i] < th) ++cnt;
+  return blk_sum_i(c, cnt);
+}
+
+}  // namespace dg

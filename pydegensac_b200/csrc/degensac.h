@@ -1,0 +1,530 @@
+// degensac.h -- DEGENSAC: H-degeneracy test of a 7-point sample, plane consensus + LO of the plane
+// homography, plane-and-parallax recovery of F.  Replaces DegUtils.c (checksample :42, Hdetect :93,
+// dHDs :186, rFtH :254, innerFH :488, dual_sample :596, u2Fit :635, innerH :693) and the old LO it
+// reaches in ranH.c (iterH :18, inHrani :88).
+//
+// B200 mapping: the 5 sample triplets of checksample are tested by 5 warps in parallel (first success in
+// triplet order wins, as in the reference's sequential loop); every O(N) pass (plane consensus, residual
+// rows, masks, ordered compactions) is CTA-parallel; the plane-and-parallax loop (<= 20k two-point
+// samples, each a Sampson pass over the off-plane correspondences) runs as speculative waves of one WARP
+// per two-point hypothesis with an ordered replay of the rare "new best" events, mirroring the main loop.
+#pragma once
+#include "common.h"
+#include "rng.h"
+#include "la.h"
+#include "fgeom.h"
+#include "hgeom.h"
+#include "block.h"
+#include "ffit.h"
+#include "hfit.h"
+
+namespace dg {
+
+// ------------------------------------------------------------------------------------------------
+// Homography compatible with F through 3 correspondences (Hartley & Zisserman p.318; reference Hdetect,
+// DegUtils.c:93-161).  u7 holds the sample as 7 x (x1,y1,x2,y2); H is column-major, image2 -> image1.
+// ------------------------------------------------------------------------------------------------
+DG_HD void h_from_F_3pts(const double* F, const double* u7, const int* tri, double* H) {
+  double ec[3];
+  right_null3(F, ec);  // F ec = 0 : third right singular vector of the row-major F
+  const double Ex[9] = {0, -ec[2], ec[1], ec[2], 0, -ec[0], -ec[1], ec[0], 0};
+  double A[9];  // A = [ec]x * F^T
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += Ex[3 * i + k] * F[3 * j + k];
+      A[3 * i + j] = s;
+    }
+  double b[3], M[9];
+  for (int t = 0; t < 3; ++t) {
+    const double* p = u7 + 4 * tri[t];
+    const double a1[3] = {p[0], p[1], 1.0};
+    const double a2[3] = {p[2], p[3], 1.0};
+    double Ab[3], p1[3], p2[3];
+    for (int i = 0; i < 3; ++i) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += A[3 * i + k] * a2[k];
+      Ab[i] = s;
+    }
+    cross3(p1, a1, Ab);
+    for (int i = 0; i < 3; ++i) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += (-Ex[3 * i + k]) * a1[k];
+      p2[i] = s;
+    }
+    b[t] = (p1[0] * p2[0] + p1[1] * p2[1] + p1[2] * p2[2]) / (p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
+    M[3 * t] = a2[0]; M[3 * t + 1] = a2[1]; M[3 * t + 2] = a2[2];
+  }
+  const int sing = inv3(M);
+  double v[3];
+  for (int i = 0; i < 3; ++i) v[i] = M[3 * i] * b[0] + M[3 * i + 1] * b[1] + M[3 * i + 2] * b[2];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) H[i + 3 * j] = A[3 * i + j] - ec[i] * v[j];
+  if (isnan(H[0]) || isinf(H[0]) || sing) {
+    for (int i = 0; i < 9; ++i) H[i] = 0.0;
+    H[0] = H[4] = H[8] = 1.0;
+  }
+}
+
+// One-thread normalised DLT on a handful of points given explicitly (the 5-point refit of checksample).
+DG_HD void h_fit_small(const double* u7, const int* idx, int len, double* h) {
+  double A1[3] = {0, 0, 0}, A2[3] = {0, 0, 0};
+  for (int j = 0; j < len; ++j) {
+    const double* p = u7 + 4 * idx[j];
+    A1[1] += p[0]; A1[2] += p[1]; A2[1] += p[2]; A2[2] += p[3];
+  }
+  for (int i = 1; i < 3; ++i) { A1[i] /= len; A2[i] /= len; }
+  for (int j = 0; j < len; ++j) {
+    const double* p = u7 + 4 * idx[j];
+    double a = p[0] - A1[1], b = p[1] - A1[2];
+    A1[0] += sqrt(a * a + b * b);
+    a = p[2] - A2[1]; b = p[3] - A2[2];
+    A2[0] += sqrt(a * a + b * b);
+  }
+  if (A1[0] != 0) A1[0] = len * sqrt(2.0) / A1[0];
+  if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
+  A1[1] *= -A1[0]; A1[2] *= -A1[0];
+  A2[1] *= -A2[0]; A2[2] *= -A2[0];
+  double C[81];
+  for (int i = 0; i < 81; ++i) C[i] = 0.0;
+  for (int j = 0; j < len; ++j) {
+    const double* p = u7 + 4 * idx[j];
+    double a[3], b[3], r0[9], r1[9];
+    a[0] = p[0] * A1[0] + A1[1]; a[1] = p[1] * A1[0] + A1[2]; a[2] = 1.0;
+    b[0] = p[2] * A2[0] + A2[1]; b[1] = p[3] * A2[0] + A2[2]; b[2] = 1.0;
+    for (int t = 0; t < 3; ++t) {
+      r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
+      r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
+    }
+    for (int i = 0; i < 9; ++i)
+      for (int jj = 0; jj <= i; ++jj) {
+        C[9 * i + jj] += r0[i] * r0[jj];
+        C[9 * i + jj] += r1[i] * r1[jj];
+      }
+  }
+  for (int i = 0; i < 9; ++i)
+    for (int jj = 0; jj < i; ++jj) C[9 * jj + i] = C[9 * i + jj];
+  min_eigvec9(C, h);
+  denorm_H(h, A1, A2);
+}
+
+// One triplet of the degeneracy test (body of the loop in checksample, DegUtils.c:55-80).
+DG_HD bool checksample_triplet(const double* F, const double* u7, int t, double th, double* H) {
+  const int TRI[5][3] = {{0, 1, 2}, {3, 4, 5}, {0, 1, 6}, {3, 4, 6}, {2, 5, 6}};
+  h_from_F_3pts(F, u7, TRI[t], H);
+  double Ds[7];
+  int idx[7];
+  for (int j = 0; j < 7; ++j) {
+    Ds[j] = h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]);
+    idx[j] = j;
+  }
+  for (int i = 0; i < 7; ++i)      // exchange sort of the reference's sortDs (DegUtils.c:164-183)
+    for (int j = i + 1; j < 7; ++j)
+      if (Ds[j] < Ds[i]) {
+        const double td = Ds[j]; Ds[j] = Ds[i]; Ds[i] = td;
+        const int ti = idx[j]; idx[j] = idx[i]; idx[i] = ti;
+      }
+  h_fit_small(u7, idx, 5, H);
+  int cnt = 0;
+  for (int j = 0; j < 7; ++j)
+    if (h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]) < th) ++cnt;
+  return cnt > 4;
+}
+
+// checksample: 5 warps test the 5 triplets concurrently; the first successful triplet (reference order)
+// provides H.  Returns the verdict to every thread, H in every thread's copy.
+DG_ENG inline bool blk_checksample(const Ctx& c, const double* F, const double* u7, double th, double* H) {
+  DG_SYNC();
+  const int par = (c.nw >= 5) ? 5 : 1;
+  if (c.lane == 0 && c.wid < par) {
+    for (int t = c.wid; t < 5; t += par) {
+      double Ht[9];
+      const bool ok = checksample_triplet(F, u7, t, th, Ht);
+      c.sc->bci[t] = ok ? 1 : 0;
+      if (t < 3) { for (int i = 0; i < 9; ++i) c.sc->bc[9 * t + i] = Ht[i]; }
+      else { for (int i = 0; i < 9; ++i) c.sc->vec[9 * (t - 3) + i] = Ht[i]; }
+    }
+  }
+  DG_SYNC();
+  int win = -1;
+  for (int t = 0; t < 5; ++t)
+    if (c.sc->bci[t]) { win = t; break; }
+  // the reference leaves the LAST tested triplet's H in the buffer when none succeeds; it is unused then
+  const int src = win < 0 ? 4 : win;
+  for (int i = 0; i < 9; ++i) H[i] = (src < 3) ? c.sc->bc[9 * src + i] : c.sc->vec[9 * (src - 3) + i];
+  DG_SYNC();
+  return win >= 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LO of the plane homography: reference innerH (DegUtils.c:693-731) -> inHrani / iterH (ranH.c:88,18),
+// Sampson metric, threshold 16*th, inlLimit = 10.  Uses its own four residual rows (W.dtmp[0..3]).
+// Writes the plane-inlier mask, returns its population.
+// ------------------------------------------------------------------------------------------------
+DG_ENG inline Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** rows, int* inl, double th, double ths,
+                                 double* Hio, unsigned inlLimit, DrawCursor& cur) {
+  int d = e[1];
+  double h[9];
+  const double dth = (ths - th) / kIlsqIters;
+  Score S = make_score(), Ss, maxS;
+  maxS = blk_inlidxs(c, rows[e[4]], th, inl);
+  if (maxS.I < 4) return S;
+  for (int i = 0; i < 9; ++i) h[i] = Hio[i];
+  if (maxS.I <= inlLimit) {
+    blk_fit_H(c, inl, (int)maxS.I, h);
+  } else {
+    blk_randsubset(c, inl, (int)maxS.I, (int)inlLimit, cur);
+    blk_fit_H(c, inl + maxS.I - inlLimit, (int)inlLimit, h);
+  }
+  for (int it = 0; it < kIlsqIters; ++it) {
+    blk_resid_H_sampson(c, h, rows[d]);
+    S = blk_inlidxs(c, rows[d], th, inl);
+    Ss = blk_inlidxs(c, rows[d], ths, inl);
+    if (score_less(maxS, S)) {
+      maxS = S;
+      e[1] = e[0];
+      e[0] = d;
+      d = e[1];
+      for (int i = 0; i < 9; ++i) Hio[i] = h[i];
+    }
+    if (Ss.I < 4) return maxS;
+    if (Ss.I <= inlLimit) {
+      blk_fit_H(c, inl, (int)Ss.I, h);
+    } else {
+      blk_randsubset(c, inl, (int)Ss.I, (int)inlLimit, cur);
+      blk_fit_H(c, inl + Ss.I - inlLimit, (int)inlLimit, h);
+    }
+    ths -= dth;
+  }
+  blk_resid_H_sampson(c, h, rows[d]);
+  S = blk_inlidxs(c, rows[d], th, inl);
+  if (score_less(maxS, S)) {
+    maxS = S;
+    e[1] = e[0];
+    e[0] = d;
+    for (int i = 0; i < 9; ++i) Hio[i] = h[i];
+  }
+  return maxS;
+}
+
+DG_ENG inline unsigned blk_inner_H(const Ctx& c, Workspace& W, double* H, double th, unsigned inlLimit,
+                                   unsigned char* mask, DrawCursor& cur) {
+  double* rows[4] = {W.dtmp[0], W.dtmp[1], W.dtmp[2], W.dtmp[3]};
+  int e[5] = {0, 1, 2, 3, 3};
+  int* inliers = W.itmp[0];
+  int* intbuff = W.itmp[1];
+  blk_resid_H_sampson(c, H, rows[e[0]]);
+  Score S = blk_inlidxs(c, rows[e[0]], th, inliers);
+  const int ninl = (int)S.I;
+  if (ninl >= 8) {  // inHrani
+    Score maxS = make_score();
+    int ssiz = ninl / 2;
+    if (ssiz > 12) ssiz = 12;
+    int t = e[2]; e[2] = e[0]; e[0] = t;
+    double h[9];
+    for (int i = 0; i < 9; ++i) h[i] = H[i];
+    for (int rep = 0; rep < kRanRep; ++rep) {
+      blk_randsubset(c, inliers, ninl, ssiz, cur);
+      blk_fit_H(c, inliers + ninl - ssiz, ssiz, h);
+      blk_resid_H_sampson(c, h, rows[e[0]]);
+      e[4] = e[0];
+      S = plane_iter_H(c, W, e, rows, intbuff, th, kTC * th, h, inlLimit, cur);
+      if (score_less(maxS, S)) {
+        maxS = S;
+        t = e[2]; e[2] = e[0]; e[0] = t;
+        for (int i = 0; i < 9; ++i) H[i] = h[i];
+      }
+    }
+    t = e[2]; e[2] = e[0]; e[0] = t;
+  }
+  const double* d = rows[e[0]];
+  int cnt = 0;
+  for (int j = c.tid; j < c.N; j += c.nt) {
+    const unsigned char m = (d[j] <= th) ? 1 : 0;
+    mask[j] = m;
+    cnt += m;
+  }
+  const int I = blk_sum_i(c, cnt);
+  DG_SYNC();
+  return (unsigned)I;
+}
+
+// ordered compaction of {i : flag(i)} into list; returns count
+template <class Pred>
+DG_ENG inline int blk_compact(const Ctx& c, int n, int* list, Pred pred) {
+  const int per = (n + c.nt - 1) / c.nt;
+  const int beg = c.tid * per;
+  const int end = (beg + per < n) ? beg + per : n;
+  int cnt = 0;
+  for (int i = beg; i < end; ++i)
+    if (pred(i)) ++cnt;
+  int total;
+  int off = blk_excl_scan_i(c, cnt, &total);
+  for (int i = beg; i < end; ++i)
+    if (pred(i)) list[off++] = i;
+  DG_SYNC();
+  return total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Iterated LSQ of F on all inliers with shrinking strict threshold (reference u2Fit, DegUtils.c:635-690).
+// F in/out; mask out; returns population.  Ds row = W.dtmp[5], list = W.itmp[3].
+// ------------------------------------------------------------------------------------------------
+DG_ENG inline unsigned blk_u2Fit(const Ctx& c, Workspace& W, double* F, unsigned char* mask, double th, double ths,
+                                 unsigned iters) {
+  const double dth = (ths - th) / (iters - 1);
+  double* Ds = W.dtmp[5];
+  int* inlI = W.itmp[3];
+  for (unsigned iter = 0; iter < iters; ++iter) {
+    blk_resid_F(c, F_SAMPSON, F, Ds);
+    const double tcur = ths;
+    int cnt = 0;
+    for (int i = c.tid; i < c.N; i += c.nt) {
+      const unsigned char m = (Ds[i] < tcur) ? 1 : 0;
+      mask[i] = m;
+      cnt += m;
+    }
+    const int no_i = blk_sum_i(c, cnt);
+    DG_SYNC();
+    if (no_i < 8) return (unsigned)no_i;
+    blk_compact(c, c.N, inlI, [&](int i) { return mask[i] != 0; });
+    blk_fit_F(c, inlI, no_i, nullptr, F);
+    ths -= dth;
+  }
+  blk_resid_F(c, F_SAMPSON, F, Ds);
+  int cnt = 0;
+  for (int i = c.tid; i < c.N; i += c.nt) {
+    const unsigned char m = (Ds[i] < th) ? 1 : 0;
+    mask[i] = m;
+    cnt += m;
+  }
+  const int no_i = blk_sum_i(c, cnt);
+  DG_SYNC();
+  return (unsigned)no_i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LO of F from plane + off-plane correspondences (reference innerFH + dual_sample, DegUtils.c:488-632).
+// uH list (plane inliers, nH), uO list (off-plane support, nO), 15 reps of 6 + 4 points.
+// Output: F (9) and inlier mask `inl` (N).  Scratch masks: W.btmp[2] (v).  Returns nothing (max_i unused).
+// ------------------------------------------------------------------------------------------------
+DG_ENG inline void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, const int* uO, int nO, double th,
+                                double* F, unsigned char* inl, DrawCursor& cur) {
+  unsigned char* v = W.btmp[2];
+  double* Ds = W.dtmp[5];
+  int* usam = W.itmp[2];  // 10 indices
+  unsigned max_i = 0, max_s = 0;
+  for (int i = 0; i < 9; ++i) F[i] = 1.0;
+  for (int i = c.tid; i < c.N; i += c.nt) inl[i] = 0;
+  DG_SYNC();
+  for (unsigned rep = 0; rep < 15; ++rep) {
+    // dual_sample: fresh identity permutations, `pos <-> rand()%len` swaps (DegUtils.c:596-632)
+    DG_SYNC();
+    if (c.tid == 0) {
+      DrawCursor t = cur;
+      int tp[12], tv[12], nt;
+      for (int side = 0; side < 2; ++side) {
+        const int len = side ? nO : nH, s = side ? 4 : 6;
+        const int* src = side ? uO : uH;
+        nt = 0;
+        for (int pos = 0; pos < s; ++pos) {
+          const int idx = (int)(next_draw(t) % (uint32_t)len);
+          int vp = pos, vi = idx;
+          for (int q = 0; q < nt; ++q) { if (tp[q] == pos) vp = tv[q]; if (tp[q] == idx) vi = tv[q]; }
+          int q = 0;
+          while (q < nt && tp[q] != pos) ++q;
+          if (q == nt) { tp[nt] = pos; ++nt; }
+          tv[q] = vi;
+          q = 0;
+          while (q < nt && tp[q] != idx) ++q;
+          if (q == nt) { tp[nt] = idx; ++nt; }
+          tv[q] = vp;
+        }
+        for (int pos = 0; pos < s; ++pos) {
+          int vp = pos;
+          for (int q = 0; q < nt; ++q) if (tp[q] == pos) vp = tv[q];
+          usam[(side ? 6 : 0) + pos] = src[vp];
+        }
+      }
+    }
+    cur.j += 10;
+    DG_SYNC();
+    double aF[9];
+    blk_fit_F(c, usam, 10, nullptr, aF);
+    blk_resid_F(c, F_SAMPSON, aF, Ds);
+    int cnt = 0;
+    for (int i = c.tid; i < c.N; i += c.nt) {
+      const unsigned char m = (Ds[i] < th) ? 1 : 0;
+      v[i] = m;
+      cnt += m;
+    }
+    unsigned no_i = (unsigned)blk_sum_i(c, cnt);
+    DG_SYNC();
+    if (max_i < no_i) {
+      for (int i = c.tid; i < c.N; i += c.nt) inl[i] = v[i];
+      for (int i = 0; i < 9; ++i) F[i] = aF[i];
+      max_i = no_i;
+      DG_SYNC();
+    }
+    if (no_i > max_s) {
+      max_s = no_i;
+      no_i = blk_u2Fit(c, W, aF, v, th, th * 3, 4);
+      if (max_i < no_i) {
+        for (int i = c.tid; i < c.N; i += c.nt) inl[i] = v[i];
+        for (int i = 0; i < 9; ++i) F[i] = aF[i];
+        max_i = no_i;
+        DG_SYNC();
+      }
+    }
+  }
+}
+
+// F = transpose( [e]x * H^T ) for the epipole e through two off-plane correspondences
+// (reference rFtH inner loop, DegUtils.c:353-371).  H column-major.
+DG_HD void f_from_plane_parallax(const double* H, double ax1, double ay1, double ax2, double ay2, double bx1,
+                                 double by1, double bx2, double by2, double* F) {
+  double ua[3] = {ax1, ay1, 1.0}, ub[3] = {bx1, by1, 1.0}, ha[3], hb[3], c1[3], c2[3], ec[3];
+  ha[0] = H[0] * ax2 + H[3] * ay2 + H[6] * 1.0;
+  ha[1] = H[1] * ax2 + H[4] * ay2 + H[7] * 1.0;
+  ha[2] = H[2] * ax2 + H[5] * ay2 + H[8] * 1.0;
+  hb[0] = H[0] * bx2 + H[3] * by2 + H[6] * 1.0;
+  hb[1] = H[1] * bx2 + H[4] * by2 + H[7] * 1.0;
+  hb[2] = H[2] * bx2 + H[5] * by2 + H[8] * 1.0;
+  cross3(c1, ua, ha);
+  cross3(c2, ub, hb);
+  cross3(ec, c1, c2);
+  const double n = sqrt(ec[0] * ec[0] + ec[1] * ec[1] + ec[2] * ec[2]);
+  ec[0] = ec[0] / n; ec[1] = ec[1] / n; ec[2] = ec[2] / n;
+  const double S[9] = {0, -ec[2], ec[1], ec[2], 0, -ec[0], -ec[1], ec[0], 0};
+  // Ht (row-major transpose of the column-major array, i.e. Ht[i][j] = H[j*3+i]); G = S * Ht ; F = G^T
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += S[3 * i + k] * H[j * 3 + k];
+      F[3 * j + i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plane-and-parallax: reference rFtH (DegUtils.c:254-444).  hinl = plane-inlier mask (from innerH).
+// Returns max_i; F written only when a better model was found (as in the reference).
+// ------------------------------------------------------------------------------------------------
+DG_ENG inline unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl, double th, const double* H,
+                                double* F, DrawCursor& cur) {
+  double* Ds = W.dtmp[4];
+  unsigned char* nhinl = W.btmp[1];
+  unsigned char* inl = W.btmp[3];
+  int* uN = W.inliers;        // ordered off-plane indices (main-loop lists are dead at this point)
+  int* uHl = W.intbuff;       // ordered plane-inlier indices
+  int* uV = W.intbuff_best;   // ordered support of the current 2-point model
+  int* ptr = W.itmp[0];       // persistent permutation over uN positions (innerH's list is dead here)
+  blk_resid_H_sampson(c, H, Ds);
+  for (int i = c.tid; i < c.N; i += c.nt) nhinl[i] = (Ds[i] > 100 * th) ? 1 : 0;
+  DG_SYNC();
+  const int nN = blk_compact(c, c.N, uN, [&](int i) { return nhinl[i] != 0; });
+  const int nH = blk_compact(c, c.N, uHl, [&](int i) { return hinl[i] != 0; });
+  unsigned max_i = 3, m_i = 4, max_sam = 10000, maxni = 0;
+  if (nN < 4 || nH < 6) return 0;
+  for (int i = c.tid; i < nN; i += c.nt) ptr[i] = i;
+  DG_SYNC();
+  const double th2 = th * 2;
+  const int WAVE = c.nw * 8;
+  int* pairs = W.itmp[2] + 16;   // WAVE x 2 sampled positions
+  int* counts = W.itmp[2] + 16 + 2 * 128;
+  unsigned no_sam = 1;
+  while (no_sam < 2 * max_sam) {
+    int nw = (int)(2 * max_sam - no_sam);
+    if (nw > WAVE) nw = WAVE;
+    if (nw > 128) nw = 128;
+    // thread 0 advances the persistent permutation speculatively for nw iterations
+    DG_SYNC();
+    if (c.tid == 0) {
+      DrawCursor t = cur;
+      for (int s = 0; s < nw; ++s) {
+        for (int pos = 0; pos < 2; ++pos) {
+          const int idx = pos + 1 + (int)(next_draw(t) % (uint32_t)(nN - pos - 1));
+          const int a = ptr[pos]; ptr[pos] = ptr[idx]; ptr[idx] = a;
+        }
+        pairs[2 * s] = ptr[0];
+        pairs[2 * s + 1] = ptr[1];
+      }
+    }
+    DG_SYNC();
+    // one warp per two-point hypothesis: support count over the off-plane correspondences
+    for (int s = c.wid; s < nw; s += c.nw) {
+      const int a = uN[pairs[2 * s]], b = uN[pairs[2 * s + 1]];
+      double aF[9];
+      f_from_plane_parallax(H, c.x1[a], c.y1[a], c.x2[a], c.y2[a], c.x1[b], c.y1[b], c.x2[b], c.y2[b], aF);
+      int cnt = 0;
+#if DG_DEVICE_PASS
+      for (int i = c.lane; i < nN; i += 32) {
+#else
+      for (int i = 0; i < nN; ++i) {
+#endif
+        const int p = uN[i];
+        if (f_resid_sampson(aF, c.x1[p], c.y1[p], c.x2[p], c.y2[p]) < th2) ++cnt;
+      }
+      cnt = warp_sum_i(cnt);
+      if (c.lane == 0) counts[s] = cnt;
+    }
+    DG_SYNC();
+    int ev = -1;
+    for (int s = 0; s < nw; ++s)
+      if ((unsigned)counts[s] > m_i) { ev = s; break; }
+    if (ev < 0) {
+      cur.j += 2u * (uint32_t)nw;
+      no_sam += (unsigned)nw;
+      continue;
+    }
+    // rewind the permutation to the state right after iteration `ev` (undo swaps ev+1..nw-1 in reverse)
+    DG_SYNC();
+    if (c.tid == 0) {
+      DrawCursor t = cur;
+      t.j += 2u * (uint32_t)(ev + 1);
+      int idxs[2 * 128];
+      for (int s = ev + 1; s < nw; ++s)
+        for (int pos = 0; pos < 2; ++pos) idxs[2 * s + pos] = pos + 1 + (int)(next_draw(t) % (uint32_t)(nN - pos - 1));
+      for (int s = nw - 1; s > ev; --s)
+        for (int pos = 1; pos >= 0; --pos) {
+          const int idx = idxs[2 * s + pos];
+          const int a = ptr[pos]; ptr[pos] = ptr[idx]; ptr[idx] = a;
+        }
+    }
+    DG_SYNC();
+    cur.j += 2u * (uint32_t)(ev + 1);
+    no_sam += (unsigned)(ev + 1);
+    // event: new best two-point support -> LO from plane + parallax points
+    {
+      const int a = uN[pairs[2 * ev]], b = uN[pairs[2 * ev + 1]];
+      double aF[9];
+      f_from_plane_parallax(H, c.x1[a], c.y1[a], c.x2[a], c.y2[a], c.x1[b], c.y1[b], c.x2[b], c.y2[b], aF);
+      const int no_i = blk_compact(c, nN, uV, [&](int i) {
+        const int p = uN[i];
+        return f_resid_sampson(aF, c.x1[p], c.y1[p], c.x2[p], c.y2[p]) < th2;
+      });
+      // uV currently holds POSITIONS in uN; convert to correspondence indices
+      for (int i = c.tid; i < no_i; i += c.nt) uV[i] = uN[uV[i]];
+      DG_SYNC();
+      m_i = (unsigned)no_i;
+      double Fnew[9];
+      blk_inner_FH(c, W, uHl, nH, uV, no_i, th, Fnew, inl, cur);
+      int cnt = 0, cnt2 = 0;
+      for (int i = c.tid; i < c.N; i += c.nt) {
+        if (inl[i]) { ++cnt; if (nhinl[i]) ++cnt2; }
+      }
+      const unsigned ninl = (unsigned)blk_sum_i(c, cnt);
+      const unsigned both = (unsigned)blk_sum_i(c, cnt2);
+      if (ninl > max_i) {
+        max_i = ninl;
+        for (int i = 0; i < 9; ++i) F[i] = Fnew[i];
+        maxni = both;
+        const unsigned ns = (unsigned)nsamples((int)maxni, nN, 2, 0.999);
+        if (ns < max_sam) max_sam = ns;
+      }
+    }
+  }
+  (void)maxni;
+  return max_i;
+}
+
+}  // namespace dg

@@ -1,0 +1,495 @@
+// engine_f.h -- LO-RANSAC / DEGENSAC for the fundamental matrix, one CTA per image pair.
+//
+// Replaces the reference's sequential driver exp_ransacFcustomLAF (exp_ranF.c:1244-1767) and its LO
+// (exp_inFranicustom :745-806, exp_iterFcustom :621-743) by a two-phase design:
+//
+//   WAVE   (parallel, speculative)  a chunk of iterations is hypothesised at once: one THREAD draws the
+//          Philox sample, solves the 7-point problem in registers/local memory and applies the oriented
+//          epipolar test; surviving models are queued and one WARP per model scores them over all
+//          correspondences in shared memory (lane-strided, shuffle reduction).  Only models whose MSAC
+//          score can beat the running thresholds survive the wave.
+//   REPLAY (ordered, exact)         survivors are re-evaluated in iteration order with the reference's
+//          control flow: so-far-the-best bookkeeping, symmetric gate, LO scheduling (first-50 rule),
+//          iterated re-weighted 8-point LSQ with hash de-duplication, adaptive termination.
+//
+// Why this is equivalent: WHICH models get scored depends only on the sampling stream; the running best
+// only decides acceptance / LO / termination (exp_ranF.c:1381-1499,1571-1576), and a model can change
+// state only if J > min(best.J, bestSample.J), a bound that never decreases inside a chunk (if it
+// does -- DEGENSAC branch -- the chunk is re-waved).  The first ITER_SAM iterations are replayed
+// unfiltered because the reference's forced LO at sample 50 reads a residual row that later models of
+// the same root index have overwritten (errs[4] aliasing, exp_ranF.c:1375,1486,1497-1508).
+#pragma once
+#include "common.h"
+#include "rng.h"
+#include "la.h"
+#include "fgeom.h"
+#include "block.h"
+#include "ffit.h"
+#include "hfit.h"
+#include "degensac.h"
+
+namespace dg {
+
+// ------------------------------------------------------------------------------ LO hash table
+// The reference de-duplicates LO inlier sets with SuperFastHash + a 64-bucket chained table
+// (hash.c:49-96, exp_ranF.c:675-686).  Only "(hash,len) seen under this iterID / another iterID /
+// never" matters, so a flat list is equivalent.  Returns true when the refinement must abort.
+DG_ENG inline bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
+  DG_SYNC();
+  if (c.tid == 0) {
+    const uint32_t h = superfasthash_i32(list, n);
+    int same = 0, other = 0;
+    for (int i = 0; i < ht.n; ++i) {
+      if (W.hhash[i] == h && W.hlen[i] == n) {
+        if (W.hid[i] == iterID) same = 1; else other = 1;
+      }
+    }
+    int verdict = 0;  // 0: insert, 1: already ours, 2: abort
+    if (same) verdict = 1; else if (other) verdict = 2;
+    if (verdict == 0 && ht.n < W.hcap) { W.hhash[ht.n] = h; W.hlen[ht.n] = n; W.hid[ht.n] = iterID; }
+    c.sc->bci[0] = verdict;
+  }
+  DG_SYNC();
+  const int verdict = c.sc->bci[0];
+  DG_SYNC();
+  if (verdict == 0 && ht.n < W.hcap) ++ht.n;
+  return verdict == 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Iterated re-weighted LSQ with shrinking threshold (reference exp_iterFcustom, exp_ranF.c:621-743).
+// e[] are the physical ids behind the reference's errs[] pointers; e[4] holds the residual row of the
+// starting model.  With the binding's inlLimit=0 every fit uses a random 8-subset.
+// ---------------------------------------------------------------------------------------------
+DG_ENG inline Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int* e, int* inl, double th,
+                              double ths, double* Fio, int iterID, DrawCursor& cur, HashTab& ht) {
+  int d = e[1];
+  double f[9];
+  const double dth = (ths - th) / kIlsqIters;
+  Score S = make_score(), Ss, maxS;
+  maxS = blk_inlidxs(c, W.err[e[4]], th, inl);
+  if (maxS.I < 8) return S;
+  S = blk_inlidxs(c, W.err[e[4]], th * kMWM, inl);
+  if (8 >= S.I) {
+    blk_fit_F(c, inl, (int)S.I, nullptr, f);
+  } else {
+    blk_randsubset(c, inl, (int)S.I, 8, cur);
+    blk_fit_F(c, inl + S.I - 8, 8, nullptr, f);
+  }
+  for (int it = 0; it < kIlsqIters; ++it) {
+    blk_resid_w_F(c, P.metric, f, W.err[d], W.w);
+    S = blk_inlidxs(c, W.err[d], th, inl);
+    if (hash_seen_elsewhere(c, W, ht, inl, (int)S.I, iterID)) return make_score();
+    if (score_less(maxS, S)) {
+      maxS = S;
+      e[1] = e[0];
+      e[0] = d;
+      d = e[1];
+      for (int i = 0; i < 9; ++i) Fio[i] = f[i];
+    }
+    Ss = blk_inlidxs(c, W.err[d], ths * kMWM, inl);
+    if (Ss.I < 8) return maxS;
+    if (8 >= Ss.I) {
+      blk_fit_F(c, inl, (int)Ss.I, W.w, f);
+    } else {
+      blk_randsubset(c, inl, (int)Ss.I, 8, cur);
+      blk_fit_F(c, inl + Ss.I - 8, 8, W.w, f);
+    }
+    ths -= dth;
+  }
+  blk_resid_F(c, P.metric, f, W.err[d]);
+  S = blk_inlidxs(c, W.err[d], th, inl);
+  if (score_less(maxS, S)) {
+    maxS = S;
+    e[1] = e[0];
+    e[0] = d;
+    for (int i = 0; i < 9; ++i) Fio[i] = f[i];
+  }
+  return maxS;
+}
+
+// Inner RANSAC of the LO step (reference exp_inFranicustom, exp_ranF.c:745-806).
+DG_ENG inline Score lo_inner_F(const Ctx& c, const FParams& P, Workspace& W, int* e, int* inliers, int ninl,
+                               double th, double* Fout, int& iterID, DrawCursor& cur, HashTab& ht) {
+  Score S, maxS = make_score();
+  if (ninl < 16) return maxS;
+  int ssiz = ninl / 2;
+  if (ssiz > 14) ssiz = 14;
+  int t = e[2]; e[2] = e[0]; e[0] = t;
+  double f[9];
+  for (int rep = 0; rep < kRanRep; ++rep) {
+    blk_randsubset(c, inliers, ninl, ssiz, cur);
+    blk_fit_F(c, inliers + ninl - ssiz, ssiz, nullptr, f);
+    blk_resid_F(c, P.metric, f, W.err[e[0]]);
+    e[4] = e[0];
+    ++iterID;
+    S = lo_iter_F(c, P, W, e, W.intbuff, th, kTC * th, f, iterID, cur, ht);
+    if (score_less(maxS, S)) {
+      maxS = S;
+      t = e[2]; e[2] = e[0]; e[0] = t;
+      for (int i = 0; i < 9; ++i) Fout[i] = f[i];
+      for (int j = c.tid; j < (int)maxS.I; j += c.nt) W.intbuff_best[j] = W.intbuff[j];
+      DG_SYNC();
+    }
+  }
+  t = e[2]; e[2] = e[0]; e[0] = t;
+  for (int j = c.tid; j < (int)maxS.I; j += c.nt) inliers[j] = W.intbuff_best[j];
+  DG_SYNC();
+  return maxS;
+}
+
+// Running state of one pair (replicated in every thread; all values are block-uniform).
+struct FState {
+  Score maxS, maxSs;
+  int e[5];
+  double F[9], FBest[9];
+  int samidxBest[7];
+  int max_sam, iter_cnt, degen_cnt, non_degen, iterID, Ihmax;
+  HashTab ht;
+  DrawCursor cur;
+};
+
+// "LSQ before LO" + LO + acceptance (exp_ranF.c:1501-1577 in the loop, :1630-1696 post-loop).
+// src_row: residual row the LSQ support is taken from (errs[4] in the loop, errorsBest post-loop).
+DG_ENG inline bool run_lo_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, const double* src_row) {
+  double f[9];
+  bool new_max = false;
+  ++st.iter_cnt;
+  const int d = st.e[0];
+  Score S = blk_inlidxs(c, src_row, kTC * P.th * kMWM, W.inliers);
+  blk_fit_F(c, W.inliers, (int)S.I, nullptr, f);
+  blk_resid_F(c, P.metric, f, W.err[d]);
+  S = blk_inlidxs(c, W.err[d], P.th, W.inliers);
+  S = lo_inner_F(c, P, W, st.e, W.inliers, (int)S.I, P.th, f, st.iterID, st.cur, st.ht);
+  if (score_less(st.maxS, S)) {
+    bool do_update = true;
+    if (P.do_sym) {
+      S.Is = blk_sym_count_F(c, f, W.inliers, (int)S.I, P.sym_th);
+      if (S.Is < st.maxS.Is) do_update = false;
+    }
+    if (do_update) {
+      const int t = st.e[0]; st.e[0] = st.e[3]; st.e[3] = t;
+      st.maxS = S;
+      for (int i = 0; i < 9; ++i) st.F[i] = f[i];
+      new_max = true;
+    }
+  }
+  return new_max;
+}
+
+// ---------------------------------------------------------------------------------------------
+// WAVE: hypothesise iterations kbeg..kend (1-based), queue oriented-valid models, score them one
+// warp per model, keep those with J > T (or all when passall).  Returns the number kept; W.pass holds
+// their indices into W.cand sorted by (iteration, root).  valid_itersam reports whether iteration
+// ITER_SAM produced a two-dimensional null space (needed for the forced-LO rule).
+// ---------------------------------------------------------------------------------------------
+DG_ENG inline int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int kend, double T, bool passall,
+                         bool* valid_itersam) {
+  DG_SYNC();
+  if (c.tid == 0) { c.sc->counter[0] = 0; c.sc->counter[1] = 0; c.sc->counter[2] = 0; }
+  DG_SYNC();
+  // stage A: one thread per minimal sample
+  for (int k = kbeg + c.tid; k <= kend; k += c.nt) {
+    int sel[7];
+    minimal_sample<7>(P.seed, (uint32_t)k, c.N, sel);
+    double M[81], sol[81];
+    for (int i = 0; i < 7; ++i) {
+      const int p = sel[i];
+      f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], M + 9 * i);
+    }
+    for (int i = 63; i < 81; ++i) M[i] = 0.0;
+    const int nullsize = nullspace9(M, sol);
+    if (nullsize != 2) continue;
+    if (k == kIterSam) c.sc->counter[2] = 1;
+    double* f1 = sol;
+    double* f2 = sol + 9;
+    double poly[4], roots[3];
+    seven_pt_cubic(f1, f2, poly);
+    const int nsol = cubic_real_roots(poly, roots);
+    double sx1[7], sy1[7], sx2[7], sy2[7];
+    for (int t = 0; t < 7; ++t) {  // reference samidx order = reverse draw order
+      const int p = sel[6 - t];
+      sx1[t] = c.x1[p]; sy1[t] = c.y1[p]; sx2[t] = c.x2[p]; sy2[t] = c.y2[p];
+    }
+    for (int i = 0; i < nsol; ++i) {
+      double f[9];
+      for (int j = 0; j < 9; ++j) f[j] = f1[j] * roots[i] + f2[j] * (1 - roots[i]);
+      if (!oriented_ok_F(f, sx1, sy1, sx2, sy2, 7)) continue;
+      const int slot = atomic_inc_shared(&c.sc->counter[0]);
+      if (slot < W.cand_cap) {
+        Cand& cd = W.cand[slot];
+        for (int j = 0; j < 9; ++j) cd.f[j] = f[j];
+        cd.k = k;
+        cd.root = i;
+      }
+    }
+  }
+  DG_SYNC();
+  int ncand = c.sc->counter[0];
+  if (ncand > W.cand_cap) ncand = W.cand_cap;
+  *valid_itersam = (c.sc->counter[2] != 0);
+  // stage B: one warp per model, lanes stride the correspondences
+  const double w94 = P.th * 9 / 4;
+  for (int ci = c.wid; ci < ncand; ci += c.nw) {
+    bool keep = passall;
+    if (!passall) {
+      double f[9];
+      for (int j = 0; j < 9; ++j) f[j] = W.cand[ci].f[j];
+      double J = 0.0;
+#if DG_DEVICE_PASS
+      for (int i = c.lane; i < c.N; i += 32) {
+#else
+      for (int i = 0; i < c.N; ++i) {
+#endif
+        const double e = f_resid(P.metric, f, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+        if (e < w94) J += 1 - (e / w94);
+      }
+      J = warp_sum(J);
+      keep = J > T - 1e-9 * (1.0 + fabs(T));
+    }
+    if (c.lane == 0 && keep) {
+      const int slot = atomic_inc_shared(&c.sc->counter[1]);
+      W.pass[slot] = ci;
+    }
+  }
+  DG_SYNC();
+  const int npass = c.sc->counter[1];
+  // order survivors by (iteration, root): small list, thread 0 insertion sort
+  if (c.tid == 0) {
+    for (int a = 1; a < npass; ++a) {
+      const int v = W.pass[a];
+      const long key = (long)W.cand[v].k * 4 + W.cand[v].root;
+      int b = a - 1;
+      while (b >= 0) {
+        const int u = W.pass[b];
+        const long kb = (long)W.cand[u].k * 4 + W.cand[u].root;
+        if (kb <= key) break;
+        W.pass[b + 1] = u;
+        --b;
+      }
+      W.pass[b + 1] = v;
+    }
+  }
+  DG_SYNC();
+  return npass;
+}
+
+// Final inlier mask (exp_ranF.c:1699-1723) incl. the reference's indexing quirk in the symmetric prune
+// (it clears mask[j] for the j-th LIST POSITION instead of mask[inliers[j]]).
+DG_ENG inline void final_mask_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, unsigned char* mask) {
+  const double* d = W.err[st.e[3]];
+  for (int j = c.tid; j < c.N; j += c.nt) mask[j] = (d[j] <= P.th) ? 1 : 0;
+  DG_SYNC();
+  if (P.do_sym) {
+    const Score S = blk_inlidxs(c, d, P.th, W.inliers);
+    for (int j = c.tid; j < (int)S.I; j += c.nt) {
+      const int i = W.inliers[j];
+      if (f_resid_symepi(st.F, c.x1[i], c.y1[i], c.x2[i], c.y2[i]) > P.sym_th) mask[j] = 0;
+    }
+    DG_SYNC();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// REPLAY of one iteration (the body of the reference's while loop, exp_ranF.c:1334-1578) restricted to
+// the models that survived the wave (`cnt` entries of W.pass starting at `pos`, ascending root order).
+// ---------------------------------------------------------------------------------------------
+DG_ENG inline void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, int k, int pos,
+                                      int cnt) {
+  bool new_max = false, do_iterate = false;
+  int sel[7], samidx[7];
+  minimal_sample<7>(P.seed, (uint32_t)k, c.N, sel);
+  for (int t = 0; t < 7; ++t) samidx[t] = sel[6 - t];
+  st.cur.seed = P.seed; st.cur.k = (uint32_t)k; st.cur.j = 8;
+  for (int q = 0; q < cnt; ++q) {
+    const Cand& cd = W.cand[W.pass[pos + q]];
+    const int i = cd.root;
+    double f[9];
+    for (int j = 0; j < 9; ++j) f[j] = cd.f[j];
+    int d = st.e[i];
+    blk_resid_F(c, P.metric, f, W.err[d]);
+    Score S = blk_inlidxs(c, W.err[d], P.th, W.inliers);
+    if (score_less(st.maxS, S)) {
+      bool ok = true;
+      if (P.do_sym) {
+        S.Is = blk_sym_count_F(c, f, W.inliers, (int)S.I, P.sym_th);
+        if (S.Is < st.maxS.Is) ok = false;
+      }
+      if (!ok) continue;  // the reference `continue`s: the best-sample test below is skipped too
+      st.e[i] = st.e[3];
+      st.e[3] = d;
+      st.maxS = S;
+      for (int j = 0; j < 9; ++j) st.F[j] = f[j];
+      new_max = true;
+    }
+    if (score_less(st.maxSs, S)) {
+      st.maxSs = S;
+      bool degenerate = false;
+      double H[9];
+      if (P.degen) {
+        double u7[28];
+        for (int t = 0; t < 7; ++t) {
+          const int p = samidx[t];
+          u7[4 * t] = c.x1[p]; u7[4 * t + 1] = c.y1[p]; u7[4 * t + 2] = c.x2[p]; u7[4 * t + 3] = c.y2[p];
+        }
+        degenerate = blk_checksample(c, f, u7, 3 * P.th, H);
+      }
+      if (degenerate) {
+        blk_resid_H_sampson(c, H, W.dtmp[4]);
+        unsigned I = (unsigned)blk_count_lt(c, W.dtmp[4], P.th * 3);
+        if (I < 8) break;
+        I = blk_inner_H(c, W, H, 16 * P.th, 10, W.btmp[0], st.cur);
+        if ((int)I > st.Ihmax) st.Ihmax = (int)I;
+        if (I > 6) {
+          I = blk_rFtH(c, W, W.btmp[0], P.th, H, f, st.cur);
+          if (I > st.maxS.I) {
+            blk_resid_F(c, P.metric, f, W.err[st.e[3]]);
+            st.maxS.I = I;
+            for (int j = 0; j < 9; ++j) st.F[j] = f[j];
+            new_max = true;
+            d = st.e[3];
+          } else {
+            blk_resid_F(c, P.metric, f, W.err[st.e[i]]);
+            d = st.e[i];
+          }
+          double jj = 0.0;
+          {  // J of the row in index order per thread segment (exp_ranF.c:1470-1477)
+            const Score t = blk_inlidxs(c, W.err[d], P.th, W.inliers);
+            jj = t.J;
+          }
+          if (new_max) st.maxS.J = jj;
+          ++st.degen_cnt;
+        }
+      } else {
+        do_iterate = (k > kIterSam);
+        st.e[4] = d;
+        ++st.non_degen;
+        for (int t = 0; t < 7; ++t) st.samidxBest[t] = samidx[t];
+        for (int j = c.tid; j < c.N; j += c.nt) W.errBest[j] = W.err[d][j];
+        DG_SYNC();
+        for (int j = 0; j < 9; ++j) st.FBest[j] = f[j];
+      }
+    }
+  }
+  if (k == kIterSam && st.non_degen) do_iterate = true;
+  if (do_iterate) {
+    if (run_lo_F(c, P, W, st, W.err[st.e[4]])) new_max = true;
+    if (new_max) {
+      const int new_sam = nsamples((int)st.maxS.I + 1, c.N, 7, P.conf);
+      if (new_sam < st.max_sam) st.max_sam = new_sam;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One image pair, whole RANSAC.  Outputs: F (row-major, zero when no model), mask, stats
+// {samples drawn, LO runs, plane inliers (Ihmax), inlier count of the returned model}.
+// ---------------------------------------------------------------------------------------------
+DG_ENG inline void ransac_F_pair(const Ctx& c, const FParams& P, Workspace& W, double* F_out, unsigned char* mask_out,
+                                 int* stats_out) {
+  FState st;
+  st.maxS = make_score(); st.maxSs = make_score();
+  st.maxS.I = 8; st.maxSs.I = 8;
+  for (int i = 0; i < 4; ++i) st.e[i] = i;
+  st.e[4] = 3;
+  for (int i = 0; i < 9; ++i) { st.F[i] = 0.0; st.FBest[i] = 0.0; }
+  for (int i = 0; i < 7; ++i) st.samidxBest[i] = 0;
+  st.max_sam = P.max_iters; st.iter_cnt = 0; st.degen_cnt = 0; st.non_degen = 0; st.iterID = 0; st.Ihmax = 0;
+  st.ht.n = 0;
+  st.cur.seed = P.seed; st.cur.k = 0; st.cur.j = 1;
+  // residual rows start zeroed (the reference reads uninitialised malloc memory if no model is ever scored)
+  for (int r = 0; r < 4; ++r)
+    for (int j = c.tid; j < c.N; j += c.nt) W.err[r][j] = 0.0;
+  for (int j = c.tid; j < c.N; j += c.nt) W.errBest[j] = 0.0;
+  DG_SYNC();
+
+  int k0 = 0, no_sam = 0;
+  bool finished = false;
+  while (!finished && k0 < st.max_sam) {
+    int kend = k0 + P.chunk;
+    if (kend > st.max_sam) kend = st.max_sam;
+    const bool passall = k0 < kIterSam;
+    if (passall && kend > kIterSam) kend = kIterSam;
+    const double T = st.maxS.J < st.maxSs.J ? st.maxS.J : st.maxSs.J;
+    bool valid_itersam = false;
+    const int npass = wave_F(c, P, W, k0 + 1, kend, T, passall, &valid_itersam);
+    int pos = 0;
+    bool rewave = false, did_itersam = false;
+    while (pos < npass) {
+      const int k = W.cand[W.pass[pos]].k;
+      if (k > st.max_sam) break;
+      int cnt = 1;
+      while (pos + cnt < npass && W.cand[W.pass[pos + cnt]].k == k) ++cnt;
+      replay_iteration_F(c, P, W, st, k, pos, cnt);
+      if (k == kIterSam) did_itersam = true;
+      pos += cnt;
+      if (k >= st.max_sam) { finished = true; no_sam = k; break; }
+      const double Tn = st.maxS.J < st.maxSs.J ? st.maxS.J : st.maxSs.J;
+      if (Tn < T && k < kend) { rewave = true; k0 = k; break; }
+    }
+    if (finished) break;
+    if (rewave) continue;
+    if (kend == kIterSam && kIterSam <= st.max_sam && valid_itersam && !did_itersam) {
+      // iteration ITER_SAM had a valid null space but no oriented-valid model: only the forced-LO rule applies
+      replay_iteration_F(c, P, W, st, kIterSam, 0, 0);
+      if (kIterSam >= st.max_sam) { finished = true; no_sam = kIterSam; break; }
+    }
+    k0 = kend;
+  }
+  if (!finished) no_sam = st.max_sam;
+  if ((int)st.cur.k != no_sam) { st.cur.k = (uint32_t)no_sam; st.cur.j = 8; }
+
+  // post-loop LO when none ran (exp_ranF.c:1580-1697)
+  if (!st.iter_cnt && !st.degen_cnt && st.non_degen) {
+    bool degenerate = false;
+    double H[9], f[9];
+    if (P.degen) {
+      double u7[28];
+      for (int t = 0; t < 7; ++t) {
+        const int p = st.samidxBest[t];
+        u7[4 * t] = c.x1[p]; u7[4 * t + 1] = c.y1[p]; u7[4 * t + 2] = c.x2[p]; u7[4 * t + 3] = c.y2[p];
+      }
+      degenerate = blk_checksample(c, st.FBest, u7, 3 * P.th, H);
+    }
+    if (degenerate) {
+      blk_resid_H_sampson(c, H, W.dtmp[4]);
+      unsigned I = (unsigned)blk_count_lt(c, W.dtmp[4], P.th * 3);
+      if (I >= 8) I = blk_inner_H(c, W, H, 16 * P.th, 10, W.btmp[0], st.cur);
+      else { for (int j = c.tid; j < c.N; j += c.nt) W.btmp[0][j] = 0; DG_SYNC(); }
+      if ((int)I > st.Ihmax) st.Ihmax = (int)I;
+      if (I > 6) {
+        bool new_max = false;
+        for (int j = 0; j < 9; ++j) f[j] = st.FBest[j];  // the reference's `f` is whatever the last iteration left
+        I = blk_rFtH(c, W, W.btmp[0], P.th, H, f, st.cur);
+        int d;
+        if (I > st.maxS.I) {
+          blk_resid_F(c, P.metric, f, W.err[st.e[3]]);
+          st.maxS.I = I;
+          for (int j = 0; j < 9; ++j) st.F[j] = f[j];
+          new_max = true;
+          d = st.e[3];
+        } else {
+          blk_resid_F(c, P.metric, f, W.err[st.e[0]]);  // reference: errs[i] with a stale loop index
+          d = st.e[0];
+        }
+        const Score t = blk_inlidxs(c, W.err[d], P.th, W.inliers);
+        if (new_max) st.maxS.J = t.J;
+        ++st.degen_cnt;
+      }
+    } else {
+      run_lo_F(c, P, W, st, W.errBest);
+    }
+  }
+
+  final_mask_F(c, P, W, st, mask_out);
+  if (c.tid == 0) {
+    for (int i = 0; i < 9; ++i) F_out[i] = st.F[i];
+    stats_out[0] = no_sam;
+    stats_out[1] = st.iter_cnt;
+    stats_out[2] = st.Ihmax;
+    stats_out[3] = (int)st.maxS.I;
+  }
+  DG_SYNC();
+}
+
+}  // namespace dg

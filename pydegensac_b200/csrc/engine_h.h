@@ -1,0 +1,357 @@
+// engine_h.h -- LO-RANSAC for homographies, one CTA per image pair.
+//
+// Replaces the reference's exp_ransacHcustomLAF (exp_ranH.c:470-930, iter_type 4) and its LO
+// (exp_inHranicustom :415-467, exp_iterHcustom :291-411) with the same WAVE + ordered REPLAY design as
+// engine_f.h: one thread per 4-point sample (orientation test, 8x9 null space, near-singular rejection),
+// one warp per surviving model for the MSAC score, exact in-order replay of the models that can change
+// the running state.  Extra ordering rule of the H driver: the first LO is forced at the first sample
+// >= ITER_SAM that survives all rejections (exp_ranH.c:639-640), so until an LO has run the wave keeps
+// every valid model from iteration ITER_SAM-1 on.
+#pragma once
+#include "common.h"
+#include "rng.h"
+#include "la.h"
+#include "hgeom.h"
+#include "block.h"
+#include "ffit.h"
+#include "hfit.h"
+
+namespace dg {
+
+struct HParams {
+  double th, sym_th, conf, laf_coef;
+  int max_iters, metric, do_sym;
+  uint64_t seed;
+  int chunk;
+};
+
+DG_ENG inline void blk_resid_H(const Ctx& c, int metric, const double* h, double* out) {
+  HSym s;
+  if (metric != H_SAMPSON) h_sym_prepare(h, &s);
+  for (int i = c.tid; i < c.N; i += c.nt) out[i] = h_resid_metric(metric, h, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+  DG_SYNC();
+}
+// symmetric-transfer consistency count over a list (gate: always HDsSymMaxidx, exp_ranH.c:588-597)
+DG_ENG inline unsigned blk_sym_count_H(const Ctx& c, const double* h, const int* list, int n, double sym_th) {
+  HSym s;
+  h_sym_prepare(h, &s);
+  int cnt = 0;
+  for (int j = c.tid; j < n; j += c.nt) {
+    const int i = list[j];
+    if (h_resid_symmax_gate(s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]) <= sym_th) ++cnt;
+  }
+  return (unsigned)blk_sum_i(c, cnt);
+}
+
+// hash de-duplication shared with the F engine's table layout
+DG_ENG inline bool hash_seen_elsewhere_h(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
+  DG_SYNC();
+  if (c.tid == 0) {
+    const uint32_t h = superfasthash_i32(list, n);
+    int same = 0, other = 0;
+    for (int i = 0; i < ht.n; ++i)
+      if (W.hhash[i] == h && W.hlen[i] == n) { if (W.hid[i] == iterID) same = 1; else other = 1; }
+    int verdict = 0;
+    if (same) verdict = 1; else if (other) verdict = 2;
+    if (verdict == 0 && ht.n < W.hcap) { W.hhash[ht.n] = h; W.hlen[ht.n] = n; W.hid[ht.n] = iterID; }
+    c.sc->bci[0] = verdict;
+  }
+  DG_SYNC();
+  const int verdict = c.sc->bci[0];
+  DG_SYNC();
+  if (verdict == 0 && ht.n < W.hcap) ++ht.n;
+  return verdict == 2;
+}
+
+// Iterated LSQ with shrinking threshold (reference exp_iterHcustom, exp_ranH.c:291-411; inlLimit = 1e6
+// so every fit uses the whole support).
+DG_ENG inline Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, int* inl, double th, double ths,
+                              double* Hio, int iterID, HashTab& ht) {
+  int d = e[1];
+  double h[9];
+  const double dth = (ths - th) / kIlsqIters;
+  Score maxS, S = make_score(), Ss;
+  maxS = blk_inlidxs(c, W.err[e[4]], th, inl);
+  if (maxS.I < 4) return S;
+  S = blk_inlidxs(c, W.err[e[4]], th * kMWM, inl);
+  for (int i = 0; i < 9; ++i) h[i] = Hio[i];
+  blk_fit_H(c, inl, (int)S.I, h);
+  for (int it = 0; it < kIlsqIters; ++it) {
+    blk_resid_H(c, P.metric, h, W.err[d]);
+    Ss = blk_inlidxs(c, W.err[d], th, inl);
+    if (hash_seen_elsewhere_h(c, W, ht, inl, (int)Ss.I, iterID)) return make_score();
+    S = blk_inlidxs(c, W.err[d], ths * kMWM, inl);
+    if (score_less(maxS, Ss)) {
+      maxS = Ss;
+      e[1] = e[0];
+      e[0] = d;
+      d = e[1];
+      for (int i = 0; i < 9; ++i) Hio[i] = h[i];
+    }
+    if (S.I < 4) return maxS;
+    blk_fit_H(c, inl, (int)S.I, h);
+    ths -= dth;
+  }
+  blk_resid_H(c, P.metric, h, W.err[d]);
+  S = blk_inlidxs(c, W.err[d], th, inl);
+  if (score_less(maxS, S)) {
+    maxS = S;
+    e[1] = e[0];
+    e[0] = d;
+    for (int i = 0; i < 9; ++i) Hio[i] = h[i];
+  }
+  return maxS;
+}
+
+// Inner RANSAC of the LO step (reference exp_inHranicustom, exp_ranH.c:415-467).
+DG_ENG inline Score lo_inner_H(const Ctx& c, const HParams& P, Workspace& W, int* e, int* inliers, int ninl, double th,
+                               double* Hout, int& iterID, DrawCursor& cur, HashTab& ht) {
+  Score S, maxS = make_score();
+  if (ninl < 8) return maxS;
+  int ssiz = ninl / 2;
+  if (ssiz > 12) ssiz = 12;
+  int t = e[2]; e[2] = e[0]; e[0] = t;
+  double h[9];
+  for (int i = 0; i < 9; ++i) h[i] = Hout[i];
+  for (int rep = 0; rep < kRanRep; ++rep) {
+    blk_randsubset(c, inliers, ninl, ssiz, cur);
+    blk_fit_H(c, inliers + ninl - ssiz, ssiz, h);
+    blk_resid_H(c, P.metric, h, W.err[e[0]]);
+    e[4] = e[0];
+    ++iterID;
+    S = lo_iter_H(c, P, W, e, W.intbuff, th, kTC * th, h, iterID, ht);
+    if (score_less(maxS, S)) {
+      maxS = S;
+      t = e[2]; e[2] = e[0]; e[0] = t;
+      for (int i = 0; i < 9; ++i) Hout[i] = h[i];
+    }
+  }
+  t = e[2]; e[2] = e[0]; e[0] = t;
+  return maxS;
+}
+
+struct HState {
+  Score maxS, maxSs;
+  int e[5];
+  double H[9];
+  int max_sam, iter_cnt, iterID, no_rej;
+  HashTab ht;
+  DrawCursor cur;
+};
+
+// LO step of iter_type 4 with acceptance (exp_ranH.c:678-747 / :793-861). h: working model in/out.
+DG_ENG inline bool run_lo_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, double* h) {
+  bool new_max = false;
+  ++st.iter_cnt;
+  const int d = st.e[0];
+  Score S = blk_inlidxs(c, W.err[st.e[4]], kTC * P.th * kMWM, W.inliers);
+  blk_fit_H(c, W.inliers, (int)S.I, h);
+  blk_resid_H(c, P.metric, h, W.err[d]);
+  S = blk_inlidxs(c, W.err[d], P.th, W.inliers);
+  S = lo_inner_H(c, P, W, st.e, W.inliers, (int)S.I, P.th, h, st.iterID, st.cur, st.ht);
+  if (score_less(st.maxS, S) && !h_close_to_singular(h)) {
+    bool do_update = true;
+    if (P.do_sym) {
+      // the reference re-lists the inliers of row `d` (the pre-LO pointer), not of the LO result
+      const Score Sc = blk_inlidxs(c, W.err[d], P.th, W.itmp[0]);
+      S.Is = blk_sym_count_H(c, h, W.itmp[0], (int)Sc.I, P.sym_th);
+      if (S.Is < st.maxS.Is) do_update = false;
+    }
+    if (do_update) {
+      const int t = st.e[0]; st.e[0] = st.e[3]; st.e[3] = t;
+      st.maxS = S;
+      for (int i = 0; i < 9; ++i) st.H[i] = h[i];
+      new_max = true;
+    }
+  }
+  return new_max;
+}
+
+// WAVE over iterations kbeg..kend; survivors (J > T, or all valid models when passall) are left in
+// W.pass in iteration order (one model per iteration, so sorting by k suffices).
+DG_ENG inline int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int kend, double T, bool passall) {
+  DG_SYNC();
+  if (c.tid == 0) { c.sc->counter[0] = 0; c.sc->counter[1] = 0; }
+  DG_SYNC();
+  for (int k = kbeg + c.tid; k <= kend; k += c.nt) {
+    int sel[4];
+    minimal_sample<4>(P.seed, (uint32_t)k, c.N, sel);
+    double sx1[4], sy1[4], sx2[4], sy2[4], px1[4], py1[4], px2[4], py2[4];
+    for (int t = 0; t < 4; ++t) {
+      const int p = sel[t];
+      px1[t] = c.x1[p]; py1[t] = c.y1[p]; px2[t] = c.x2[p]; py2[t] = c.y2[p];
+    }
+    for (int t = 0; t < 4; ++t) { sx1[t] = px1[3 - t]; sy1[t] = py1[3 - t]; sx2[t] = px2[3 - t]; sy2[t] = py2[3 - t]; }
+    if (!oriented_ok_H(sx1, sy1, sx2, sy2)) continue;
+    double h[9];
+    if (!h_from_4pt(px1, py1, px2, py2, h)) continue;
+    if (h_close_to_singular(h)) continue;
+    const int slot = atomic_inc_shared(&c.sc->counter[0]);
+    if (slot < W.cand_cap) {
+      Cand& cd = W.cand[slot];
+      for (int j = 0; j < 9; ++j) cd.f[j] = h[j];
+      cd.k = k;
+      cd.root = 0;
+    }
+  }
+  DG_SYNC();
+  int ncand = c.sc->counter[0];
+  if (ncand > W.cand_cap) ncand = W.cand_cap;
+  const double w94 = P.th * 9 / 4;
+  for (int ci = c.wid; ci < ncand; ci += c.nw) {
+    bool keep = passall;
+    if (!passall) {
+      double h[9];
+      for (int j = 0; j < 9; ++j) h[j] = W.cand[ci].f[j];
+      HSym s;
+      if (P.metric != H_SAMPSON) h_sym_prepare(h, &s);
+      double J = 0.0;
+#if DG_DEVICE_PASS
+      for (int i = c.lane; i < c.N; i += 32) {
+#else
+      for (int i = 0; i < c.N; ++i) {
+#endif
+        const double e = h_resid_metric(P.metric, h, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+        if (e < w94) J += 1 - (e / w94);
+      }
+      J = warp_sum(J);
+      keep = J > T - 1e-9 * (1.0 + fabs(T));
+    }
+    if (c.lane == 0 && keep) {
+      const int slot = atomic_inc_shared(&c.sc->counter[1]);
+      W.pass[slot] = ci;
+    }
+  }
+  DG_SYNC();
+  const int npass = c.sc->counter[1];
+  if (c.tid == 0) {
+    for (int a = 1; a < npass; ++a) {
+      const int v = W.pass[a];
+      const int key = W.cand[v].k;
+      int b = a - 1;
+      while (b >= 0 && W.cand[W.pass[b]].k > key) { W.pass[b + 1] = W.pass[b]; --b; }
+      W.pass[b + 1] = v;
+    }
+  }
+  DG_SYNC();
+  return npass;
+}
+
+// REPLAY of one surviving iteration (exp_ranH.c:580-756).
+DG_ENG inline void replay_iteration_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, int k, const Cand& cd) {
+  double h[9];
+  for (int j = 0; j < 9; ++j) h[j] = cd.f[j];
+  st.cur.seed = P.seed; st.cur.k = (uint32_t)k; st.cur.j = 5;
+  bool new_max = false, do_iterate;
+  const int d = st.e[0];
+  blk_resid_H(c, P.metric, h, W.err[d]);
+  Score S = blk_inlidxs(c, W.err[d], P.th, W.itmp[0]);
+  if (score_less(st.maxS, S)) {
+    if (P.do_sym) {
+      S.Is = blk_sym_count_H(c, h, W.itmp[0], (int)S.I, P.sym_th);
+      if (S.Is < st.maxS.Is) return;  // `continue`: skips LO scheduling and the termination update
+    }
+    st.e[0] = st.e[3];
+    st.e[3] = d;
+    st.maxS = S;
+    new_max = true;
+    for (int j = 0; j < 9; ++j) st.H[j] = h[j];
+  }
+  if (score_less(st.maxSs, S)) {
+    do_iterate = k > kIterSam;
+    st.maxSs = S;
+    st.e[4] = d;
+  } else {
+    do_iterate = false;
+  }
+  if ((k >= kIterSam) && (st.iter_cnt == 0) && (st.maxSs.I > 4)) do_iterate = true;
+  if (do_iterate) {
+    if (run_lo_H(c, P, W, st, h)) new_max = true;
+  }
+  if (new_max) {
+    const int new_sam = nsamples((int)st.maxS.I + 1, c.N, 4, P.conf);
+    if (new_sam < st.max_sam) st.max_sam = new_sam;
+  }
+}
+
+// One image pair.  H_out is the RAW core output: column-major, maps image 2 -> image 1 (the Python
+// layer applies inv(H.T), utils.py:108).  stats {samples, LO runs, (unused), inliers of best}.
+DG_ENG inline void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double* H_out, unsigned char* mask_out,
+                                 int* stats_out) {
+  HState st;
+  st.maxS = make_score(); st.maxSs = make_score();
+  for (int i = 0; i < 4; ++i) st.e[i] = i;
+  st.e[4] = 3;
+  for (int i = 0; i < 9; ++i) st.H[i] = 0.0;
+  st.max_sam = P.max_iters; st.iter_cnt = 0; st.iterID = 0; st.no_rej = 0;
+  st.ht.n = 0;
+  st.cur.seed = P.seed; st.cur.k = 0; st.cur.j = 1;
+  for (int r = 0; r < 4; ++r)
+    for (int j = c.tid; j < c.N; j += c.nt) W.err[r][j] = 0.0;
+  DG_SYNC();
+
+  int k0 = 0, no_sam = 0;
+  bool finished = false;
+  while (!finished && k0 < st.max_sam) {
+    int kend;
+    bool passall = false;
+    if (st.iter_cnt == 0 && k0 < kIterSam - 1) {
+      kend = k0 + P.chunk;
+      if (kend > kIterSam - 1) kend = kIterSam - 1;
+    } else if (st.iter_cnt == 0) {
+      passall = true;
+      kend = k0 + 32;
+    } else {
+      kend = k0 + P.chunk;
+    }
+    if (kend > st.max_sam) kend = st.max_sam;
+    const double T = st.maxS.J < st.maxSs.J ? st.maxS.J : st.maxSs.J;
+    const int npass = wave_H(c, P, W, k0 + 1, kend, T, passall);
+    bool rewave = false;
+    for (int pos = 0; pos < npass; ++pos) {
+      const Cand& cd = W.cand[W.pass[pos]];
+      const int k = cd.k;
+      if (k > st.max_sam) break;
+      const int lo_before = st.iter_cnt;
+      replay_iteration_H(c, P, W, st, k, cd);
+      if (k >= st.max_sam) { finished = true; no_sam = k; break; }
+      if (passall && st.iter_cnt != lo_before && k < kend) { rewave = true; k0 = k; break; }
+    }
+    if (finished) break;
+    if (rewave) continue;
+    k0 = kend;
+  }
+  if (!finished) no_sam = st.max_sam;
+  if ((int)st.cur.k != no_sam) { st.cur.k = (uint32_t)no_sam; st.cur.j = 5; }
+
+  // post-loop LO if none ran (exp_ranH.c:759-862)
+  if (st.iter_cnt == 0) {
+    double h[9];
+    for (int i = 0; i < 9; ++i) h[i] = st.H[i];
+    run_lo_H(c, P, W, st, h);
+  }
+
+  const double* d = W.err[st.e[3]];
+  for (int j = c.tid; j < c.N; j += c.nt) mask_out[j] = (d[j] <= P.th) ? 1 : 0;
+  DG_SYNC();
+  if (P.do_sym) {
+    const Score Sc = blk_inlidxs(c, d, P.th, W.itmp[0]);
+    HSym s;
+    h_sym_prepare(st.H, &s);
+    for (int j = c.tid; j < (int)Sc.I; j += c.nt) {
+      const int i = W.itmp[0][j];
+      if (h_resid_symmax_gate(s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]) > P.sym_th) mask_out[i] = 0;
+    }
+    DG_SYNC();
+  }
+  if (c.tid == 0) {
+    for (int i = 0; i < 9; ++i) H_out[i] = st.H[i];
+    stats_out[0] = no_sam;
+    stats_out[1] = st.iter_cnt;
+    stats_out[2] = 0;
+    stats_out[3] = (int)st.maxS.I;
+  }
+  DG_SYNC();
+}
+
+}  // namespace dg

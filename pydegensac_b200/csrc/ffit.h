@@ -1,0 +1,184 @@
+// ffit.h -- per-pair workspace layout and CTA-cooperative F passes (residual rows, symmetric gate
+// count, random subsets, normalised 8-point fit) shared by the F engine and DEGENSAC.
+#pragma once
+#include "common.h"
+#include "rng.h"
+#include "la.h"
+#include "fgeom.h"
+#include "block.h"
+
+namespace dg {
+
+struct Cand {
+  double f[9];
+  int k;
+  int root;
+};
+
+struct Workspace {
+  double* err[4];   // the reference's four residual rows errs[0..3] (physical storage)
+  double* errBest;  // errorsBest
+  double* w;        // LSQ weights
+  double* dtmp[8];  // scratch rows (DEGENSAC / H paths)
+  int* inliers;
+  int* intbuff;
+  int* intbuff_best;
+  int* itmp[4];
+  unsigned char* btmp[4];
+  Cand* cand;
+  int* pass;
+  int cand_cap;
+  uint32_t* hhash;
+  int* hlen;
+  int* hid;
+  int hcap;
+};
+
+struct HashTab { int n; };
+
+struct FParams {
+  double th, sym_th, conf, laf_coef;
+  int max_iters, metric, degen, do_sym;
+  uint64_t seed;
+  int chunk;
+};
+
+// ------------------------------------------------------------------ block-wide passes over the pair
+DG_ENG inline void blk_resid_F(const Ctx& c, int metric, const double* F, double* out) {
+  for (int i = c.tid; i < c.N; i += c.nt) out[i] = f_resid(metric, F, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+  DG_SYNC();
+}
+DG_ENG inline void blk_resid_w_F(const Ctx& c, int metric, const double* F, double* out, double* w) {
+  for (int i = c.tid; i < c.N; i += c.nt) {
+    double e, ww;
+    f_resid_w(metric, F, c.x1[i], c.y1[i], c.x2[i], c.y2[i], &e, &ww);
+    out[i] = e;
+    w[i] = ww;
+  }
+  DG_SYNC();
+}
+// symmetric-epipolar consistency count over an index list (gate at exp_ranF.c:1383-1392)
+DG_ENG inline unsigned blk_sym_count_F(const Ctx& c, const double* F, const int* list, int n, double sym_th) {
+  int cnt = 0;
+  for (int j = c.tid; j < n; j += c.nt) {
+    const int i = list[j];
+    if (f_resid_symepi(F, c.x1[i], c.y1[i], c.x2[i], c.y2[i]) <= sym_th) ++cnt;
+  }
+  return (unsigned)blk_sum_i(c, cnt);
+}
+
+// Partial Fisher-Yates permutation of list[0..max_sz) drawing `siz` slots; the subset is the last
+// `siz` entries (reference randsubset, rtools.c:25-39).  Sequential by nature: thread 0.
+DG_ENG inline void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCursor& cur) {
+  DG_SYNC();
+  if (c.tid == 0) {
+    DrawCursor t = cur;
+    for (int i = 0; i < siz; ++i) {
+      const int s = (int)(next_draw(t) % (uint32_t)(max_sz - i));
+      const int j = max_sz - i - 1;
+      const int q = list[s];
+      list[s] = list[j];
+      list[j] = q;
+    }
+  }
+  cur.j += (uint32_t)siz;
+  DG_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------
+// F from a list of correspondences: reference u2f / u2fw (Ftools.c:350-458).
+//   len > 8 : Hartley normalisation -> 9x9 normal matrix (block reduction) -> smallest eigenvector
+//             (Jacobi) -> rank 2 -> de-normalise.
+//   len <= 8: unnormalised 9 x len system -> vector orthogonal to its columns -> rank 2.  With weights
+//             the reference scales the row-major 9x8 array with stride 9 (`scalmul(Z+i, w, 9, 9)`,
+//             Ftools.c:431), i.e. a diagonal pattern; reproduced as is.
+// Result is returned to every thread in f[9].
+// ---------------------------------------------------------------------------------------------
+DG_ENG inline void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, double* f) {
+  if (len <= 8) {
+    DG_SYNC();
+    if (c.tid == 0) {
+      double Z[72];
+      for (int i = 0; i < len; ++i) {
+        const int p = idx[i];
+        double row[9];
+        f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], row);
+        for (int r = 0; r < 9; ++r) Z[r * len + i] = row[r];
+      }
+      if (w) {
+        for (int i = 0; i < len; ++i) {
+          const double wi = w[idx[i]];
+          for (int t = 0; t < 9; ++t) {
+            const int lin = i + 9 * t;
+            if (lin < 9 * len) Z[lin] *= wi;
+          }
+        }
+      }
+      double q[9];
+      if (len > 0) left_null_9xk(Z, len, q);
+      else for (int i = 0; i < 9; ++i) q[i] = (i == 8) ? 1.0 : 0.0;
+      enforce_rank2(q);
+      for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+    }
+    bc_fetch(c, f, 9);
+    return;
+  }
+  // Hartley normalisation (reference normu, utools.c:7-51)
+  double v[kVecRed];
+  for (int i = 0; i < 4; ++i) v[i] = 0.0;
+  for (int j = c.tid; j < len; j += c.nt) {
+    const int p = idx[j];
+    v[0] += c.x1[p]; v[1] += c.y1[p]; v[2] += c.x2[p]; v[3] += c.y2[p];
+  }
+  blk_sum_vec(c, v, 4);
+  double A1[3], A2[3];
+  A1[1] = c.sc->vec_out[0] / len; A1[2] = c.sc->vec_out[1] / len;
+  A2[1] = c.sc->vec_out[2] / len; A2[2] = c.sc->vec_out[3] / len;
+  v[0] = 0.0; v[1] = 0.0;
+  for (int j = c.tid; j < len; j += c.nt) {
+    const int p = idx[j];
+    double a = c.x1[p] - A1[1], b = c.y1[p] - A1[2];
+    v[0] += sqrt(a * a + b * b);
+    a = c.x2[p] - A2[1]; b = c.y2[p] - A2[2];
+    v[1] += sqrt(a * a + b * b);
+  }
+  blk_sum_vec(c, v, 2);
+  A1[0] = c.sc->vec_out[0]; A2[0] = c.sc->vec_out[1];
+  if (A1[0] != 0) A1[0] = len * sqrt(2.0) / A1[0];
+  if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
+  A1[1] *= -A1[0]; A1[2] *= -A1[0];
+  A2[1] *= -A2[0]; A2[2] *= -A2[0];
+  // normal matrix of the normalised rows (reference lin_fmN + cov_mat, Ftools.c:300-328, utools.c:170-184)
+  for (int i = 0; i < 45; ++i) v[i] = 0.0;
+  for (int j = c.tid; j < len; j += c.nt) {
+    const int p = idx[j];
+    double a[3], b[3], row[9];
+    a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
+    b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
+    for (int k = 0; k < 3; ++k)
+      for (int l = 0; l < 3; ++l) row[3 * k + l] = a[l] * b[k];
+    const double ww = w ? w[p] : 1.0;
+    if (w) for (int k = 0; k < 9; ++k) row[k] *= ww;
+    int t = 0;
+    for (int i = 0; i < 9; ++i)
+      for (int jj = 0; jj <= i; ++jj) v[t++] += row[i] * row[jj];
+  }
+  blk_sum_vec(c, v, 45);
+  if (c.tid == 0) {
+    double C[81], q[9];
+    int t = 0;
+    for (int i = 0; i < 9; ++i)
+      for (int jj = 0; jj <= i; ++jj) {
+        const double s = c.sc->vec_out[t++];
+        C[9 * i + jj] = s;
+        C[9 * jj + i] = s;
+      }
+    min_eigvec9(C, q);
+    enforce_rank2(q);
+    denorm_F(q, A1, A2);
+    for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+  }
+  bc_fetch(c, f, 9);
+}
+
+}  // namespace dg

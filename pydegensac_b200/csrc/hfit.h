@@ -1,0 +1,96 @@
+// hfit.h -- CTA-cooperative homography LSQ and residual passes shared by the H engine and DEGENSAC.
+#pragma once
+#include "common.h"
+#include "la.h"
+#include "hgeom.h"
+#include "block.h"
+
+namespace dg {
+
+// Homography from a list of correspondences (reference u2h, Htools.c:101-133):
+//   len < 4  : nothing (h untouched);  len == 4 : exact null space (the reference's own len==4 branch
+//   transposes an 8-stride buffer as 9x9 and reads uninitialised stack, i.e. is undefined; the intended
+//   4-point solve is used here);  len > 4 : Hartley-normalised DLT, normal matrix by block reduction,
+//   smallest eigenvector (Jacobi instead of LAPACK dsyev_), de-normalisation.
+DG_ENG inline void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
+  if (len < 4) return;
+  if (len == 4) {
+    DG_SYNC();
+    if (c.tid == 0) {
+      double px1[4], py1[4], px2[4], py2[4], hh[9];
+      for (int i = 0; i < 4; ++i) {
+        const int p = idx[i];
+        px1[i] = c.x1[p]; py1[i] = c.y1[p]; px2[i] = c.x2[p]; py2[i] = c.y2[p];
+      }
+      h_from_4pt(px1, py1, px2, py2, hh);
+      for (int i = 0; i < 9; ++i) c.sc->bc[i] = hh[i];
+    }
+    bc_fetch(c, h, 9);
+    return;
+  }
+  double v[kVecRed];
+  for (int i = 0; i < 4; ++i) v[i] = 0.0;
+  for (int j = c.tid; j < len; j += c.nt) {
+    const int p = idx[j];
+    v[0] += c.x1[p]; v[1] += c.y1[p]; v[2] += c.x2[p]; v[3] += c.y2[p];
+  }
+  blk_sum_vec(c, v, 4);
+  double A1[3], A2[3];
+  A1[1] = c.sc->vec_out[0] / len; A1[2] = c.sc->vec_out[1] / len;
+  A2[1] = c.sc->vec_out[2] / len; A2[2] = c.sc->vec_out[3] / len;
+  v[0] = 0.0; v[1] = 0.0;
+  for (int j = c.tid; j < len; j += c.nt) {
+    const int p = idx[j];
+    double a = c.x1[p] - A1[1], b = c.y1[p] - A1[2];
+    v[0] += sqrt(a * a + b * b);
+    a = c.x2[p] - A2[1]; b = c.y2[p] - A2[2];
+    v[1] += sqrt(a * a + b * b);
+  }
+  blk_sum_vec(c, v, 2);
+  A1[0] = c.sc->vec_out[0]; A2[0] = c.sc->vec_out[1];
+  if (A1[0] != 0) A1[0] = len * sqrt(2.0) / A1[0];
+  if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
+  A1[1] *= -A1[0]; A1[2] *= -A1[0];
+  A2[1] *= -A2[0]; A2[2] *= -A2[0];
+  for (int i = 0; i < 45; ++i) v[i] = 0.0;
+  for (int j = c.tid; j < len; j += c.nt) {
+    const int p = idx[j];
+    double a[3], b[3], r0[9], r1[9];
+    a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
+    b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
+    for (int t = 0; t < 3; ++t) {  // reference lin_hgN, Htools.c:60-99
+      r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
+      r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
+    }
+    int t = 0;
+    for (int i = 0; i < 9; ++i)
+      for (int jj = 0; jj <= i; ++jj) {
+        v[t] += r0[i] * r0[jj];
+        v[t] += r1[i] * r1[jj];
+        ++t;
+      }
+  }
+  blk_sum_vec(c, v, 45);
+  if (c.tid == 0) {
+    double C[81], q[9];
+    int t = 0;
+    for (int i = 0; i < 9; ++i)
+      for (int jj = 0; jj <= i; ++jj) {
+        const double s = c.sc->vec_out[t++];
+        C[9 * i + jj] = s;
+        C[9 * jj + i] = s;
+      }
+    min_eigvec9(C, q);
+    denorm_H(q, A1, A2);
+    for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+  }
+  bc_fetch(c, h, 9);
+}
+
+// Sampson residual row of all correspondences under h (reference HDs over lin_hg, as dHDs does).
+DG_ENG inline void blk_resid_H_sampson(const Ctx& c, const double* h, double* out) {
+  for (int i = c.tid; i < c.N; i += c.nt) out[i] = h_resid_sampson(h, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+  DG_SYNC();
+}
+
+}  // namespace dg

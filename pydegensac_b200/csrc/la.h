@@ -1,0 +1,303 @@
+// la.h -- tiny dense linear algebra done by one thread in registers / local memory.
+// No cuSOLVER, no LAPACK: every solve on the hot path is at most 9x9.
+#pragma once
+#include "common.h"
+
+namespace dg {
+
+// ---------------------------------------------------------------------------------------------
+// Null space of a 9x9 row-major system by Gauss-Jordan elimination with partial pivoting.
+// Semantics follow the reference's `nullspace` (utools.c:97-167): column sweep, pivot searched
+// from the diagonal row downwards with strict improvement, pivots below 1e-12 declare a free
+// column, the k-th null vector is (-column of the reduced matrix ; unit on the free column).
+// Returns the number of null vectors (written to ns[k*9 + ...]).
+// ---------------------------------------------------------------------------------------------
+DG_HD int nullspace9(double* M, double* ns) {
+  const double tol = 1e-12;
+  int freec[9], pivc[9];
+  int nfree = 0, npiv = 0, row = 0;
+  for (int col = 0; col < 9; ++col) {
+    int best = row;
+    double mag = fabs(M[9 * row + col]);
+    for (int r = row + 1; r < 9; ++r) {
+      const double t = fabs(M[9 * r + col]);
+      if (mag < t) { mag = t; best = r; }
+    }
+    if (mag < tol) {
+      freec[nfree++] = col;
+      for (int r = row; r < 9; ++r) M[9 * r + col] = 0.0;
+      continue;
+    }
+    pivc[npiv++] = col;
+    if (best != row) {
+      for (int c = col; c < 9; ++c) {
+        const double t = M[9 * row + c];
+        M[9 * row + c] = M[9 * best + c];
+        M[9 * best + c] = t;
+      }
+    }
+    const double p = M[9 * row + col];
+    for (int c = col; c < 9; ++c) M[9 * row + c] /= p;
+    for (int r = 0; r < 9; ++r) {
+      if (r == row) continue;
+      const double a = M[9 * r + col];
+      for (int c = col; c < 9; ++c) M[9 * r + c] -= a * M[9 * row + c];
+    }
+    ++row;
+  }
+  for (int k = 0; k < nfree; ++k) {
+    const int j = freec[k];
+    for (int l = 0; l < npiv; ++l) ns[k * 9 + pivc[l]] = -M[l * 9 + j];
+    for (int l = 0; l < nfree; ++l) ns[k * 9 + freec[l]] = (j == freec[l]) ? 1.0 : 0.0;
+  }
+  return nfree;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Symmetric 9x9 eigen-decomposition by cyclic Jacobi rotations (replaces LAPACK dsyev_, which the
+// reference reaches through lapwrap.c:67 from u2f/u2fw/u2h).  A is destroyed; on return column k of
+// V (V[r*9+k]) is the eigenvector of d[k].  Eigenvalues are NOT sorted; callers pick the minimum.
+// ---------------------------------------------------------------------------------------------
+DG_HD void jacobi_eig9(double* A, double* V, double* d) {
+  for (int i = 0; i < 81; ++i) V[i] = 0.0;
+  for (int i = 0; i < 9; ++i) V[i * 10] = 1.0;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double off = 0.0, dia = 0.0;
+    for (int p = 0; p < 9; ++p) {
+      dia += A[p * 10] * A[p * 10];
+      for (int q = p + 1; q < 9; ++q) off += A[p * 9 + q] * A[p * 9 + q];
+    }
+    if (!(off > 1e-34 * dia) || off == 0.0) break;
+    for (int p = 0; p < 8; ++p) {
+      for (int q = p + 1; q < 9; ++q) {
+        const double apq = A[p * 9 + q];
+        if (apq == 0.0) continue;
+        const double app = A[p * 10], aqq = A[q * 10];
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 9; ++k) {  // columns p,q
+          const double akp = A[k * 9 + p], akq = A[k * 9 + q];
+          A[k * 9 + p] = c * akp - s * akq;
+          A[k * 9 + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 9; ++k) {  // rows p,q
+          const double apk = A[p * 9 + k], aqk = A[q * 9 + k];
+          A[p * 9 + k] = c * apk - s * aqk;
+          A[q * 9 + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 9; ++k) {
+          const double vkp = V[k * 9 + p], vkq = V[k * 9 + q];
+          V[k * 9 + p] = c * vkp - s * vkq;
+          V[k * 9 + q] = s * vkp + c * vkq;
+        }
+      }
+    }
+  }
+  for (int i = 0; i < 9; ++i) d[i] = A[i * 10];
+}
+
+// Eigenvector of the smallest eigenvalue of the symmetric 9x9 matrix C (destroyed) -> v[9].
+DG_HD void min_eigvec9(double* C, double* v) {
+  double V[81], d[9];
+  jacobi_eig9(C, V, d);
+  int j = 0;
+  for (int i = 1; i < 9; ++i)
+    if (d[i] < d[j]) j = i;
+  for (int i = 0; i < 9; ++i) v[i] = V[i * 9 + j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// One-sided (Hestenes) Jacobi SVD of a 3x3 row-major matrix: G = A*V has orthogonal columns whose
+// norms are the singular values.  Used for the rank-2 projection of F (reference singulF,
+// Ftools.c:330-347, LAPACK dgesvd_) and for the epipole in Hdetect (DegUtils.c:109, CCMATH svduv).
+// ---------------------------------------------------------------------------------------------
+DG_HD void svd3_onesided(const double* A, double* G, double* V, double* sv) {
+  for (int i = 0; i < 9; ++i) { G[i] = A[i]; V[i] = 0.0; }
+  V[0] = V[4] = V[8] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 2; ++p) {
+      for (int q = p + 1; q < 3; ++q) {
+        double al = 0.0, be = 0.0, ga = 0.0;
+        for (int i = 0; i < 3; ++i) {
+          al += G[3 * i + p] * G[3 * i + p];
+          be += G[3 * i + q] * G[3 * i + q];
+          ga += G[3 * i + p] * G[3 * i + q];
+        }
+        if (ga == 0.0 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+        rotated = true;
+        const double zeta = (be - al) / (2.0 * ga);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int i = 0; i < 3; ++i) {
+          const double gp = G[3 * i + p], gq = G[3 * i + q];
+          G[3 * i + p] = c * gp - s * gq;
+          G[3 * i + q] = s * gp + c * gq;
+          const double vp = V[3 * i + p], vq = V[3 * i + q];
+          V[3 * i + p] = c * vp - s * vq;
+          V[3 * i + q] = s * vp + c * vq;
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  for (int c = 0; c < 3; ++c) sv[c] = sqrt(G[c] * G[c] + G[3 + c] * G[3 + c] + G[6 + c] * G[6 + c]);
+}
+
+// Rank-2 projection F <- U diag(s0,s1,0) V^T == F - (F v_min) v_min^T   (reference: singulF)
+DG_HD void enforce_rank2(double* F) {
+  double G[9], V[9], sv[3];
+  svd3_onesided(F, G, V, sv);
+  int m = 0;
+  if (sv[1] < sv[m]) m = 1;
+  if (sv[2] < sv[m]) m = 2;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) F[3 * i + j] -= G[3 * i + m] * V[3 * j + m];
+}
+
+// Right singular vector of the smallest singular value of a 3x3 row-major matrix (A v ~ 0).
+DG_HD void right_null3(const double* A, double* v) {
+  double G[9], V[9], sv[3];
+  svd3_onesided(A, G, V, sv);
+  int m = 0;
+  if (sv[1] < sv[m]) m = 1;
+  if (sv[2] < sv[m]) m = 2;
+  v[0] = V[m]; v[1] = V[3 + m]; v[2] = V[6 + m];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Unit vector orthogonal to the `len` (<= 8) columns of the 9 x len row-major matrix Z (destroyed):
+// the last column of the full Q of a Householder QR.  This is what the reference takes from CCMATH
+// svduv as "last column of U" in the len <= 8 branch of u2f/u2fw (Ftools.c:373,383,433,443).
+// ---------------------------------------------------------------------------------------------
+DG_HD void left_null_9xk(double* Z, int len, double* q) {
+  double vs[8][9];
+  double beta[8];
+  for (int c = 0; c < len; ++c) {
+    double nrm = 0.0;
+    for (int r = c; r < 9; ++r) nrm += Z[r * len + c] * Z[r * len + c];
+    nrm = sqrt(nrm);
+    for (int r = 0; r < 9; ++r) vs[c][r] = 0.0;
+    if (nrm == 0.0) { beta[c] = 0.0; continue; }
+    const double x0 = Z[c * len + c];
+    const double alpha = (x0 >= 0.0) ? -nrm : nrm;
+    for (int r = c; r < 9; ++r) vs[c][r] = Z[r * len + c];
+    vs[c][c] = x0 - alpha;
+    double vn = 0.0;
+    for (int r = c; r < 9; ++r) vn += vs[c][r] * vs[c][r];
+    beta[c] = (vn > 0.0) ? 2.0 / vn : 0.0;
+    for (int cc = c; cc < len; ++cc) {
+      double dot = 0.0;
+      for (int r = c; r < 9; ++r) dot += vs[c][r] * Z[r * len + cc];
+      dot *= beta[c];
+      for (int r = c; r < 9; ++r) Z[r * len + cc] -= dot * vs[c][r];
+    }
+  }
+  for (int r = 0; r < 9; ++r) q[r] = 0.0;
+  q[8] = 1.0;
+  for (int c = len - 1; c >= 0; --c) {
+    double dot = 0.0;
+    for (int r = c; r < 9; ++r) dot += vs[c][r] * q[r];
+    dot *= beta[c];
+    for (int r = c; r < 9; ++r) q[r] -= dot * vs[c][r];
+  }
+}
+
+// 3x3 inverse in place (row-major) by Gauss-Jordan with partial pivoting.  Returns nonzero when a
+// pivot falls below 1e-15 x the largest pivot seen so far (the singularity rule of CCMATH minv,
+// matutls/minv.c:11,27), in which case the matrix content is unspecified.
+DG_HD int inv3(double* a) {
+  double m[3][6];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) { m[i][j] = a[3 * i + j]; m[i][3 + j] = (i == j) ? 1.0 : 0.0; }
+  double tq = 0.0;
+  for (int c = 0; c < 3; ++c) {
+    int best = c;
+    double s = fabs(m[c][c]);
+    for (int r = c + 1; r < 3; ++r) {
+      const double t = fabs(m[r][c]);
+      if (t > s) { s = t; best = r; }
+    }
+    tq = tq > s ? tq : s;
+    if (s < 1e-15 * tq || s == 0.0) return -1;
+    if (best != c)
+      for (int k = 0; k < 6; ++k) { const double t = m[c][k]; m[c][k] = m[best][k]; m[best][k] = t; }
+    const double inv = 1.0 / m[c][c];
+    for (int k = 0; k < 6; ++k) m[c][k] *= inv;
+    for (int r = 0; r < 3; ++r) {
+      if (r == c) continue;
+      const double f = m[r][c];
+      for (int k = 0; k < 6; ++k) m[r][k] -= f * m[c][k];
+    }
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) a[3 * i + j] = m[i][3 + j];
+  return 0;
+}
+
+DG_HD double det3(const double* A) {  // utools.c:196-202
+  double r = (A[0] * A[4] * A[8] + A[2] * A[3] * A[7] + A[1] * A[5] * A[6]);
+  r -= (A[2] * A[4] * A[6] + A[0] * A[5] * A[7] + A[1] * A[3] * A[8]);
+  return r;
+}
+
+DG_HD void cross3(double* o, const double* a, const double* b) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// SuperFastHash over an ordered list of int32 indices, bit-exact with hash.c:4-47 for a byte string
+// of 4*n bytes (little endian): used to de-duplicate LO inlier sets (exp_ranF.c:675-686).
+// ---------------------------------------------------------------------------------------------
+DG_HD uint32_t sfh_init(int n) { return (uint32_t)(4 * n); }
+DG_HD uint32_t sfh_word(uint32_t hash, uint32_t w) {
+  hash += (w & 0xffffu);
+  const uint32_t tmp = ((w >> 16) << 11) ^ hash;
+  hash = (hash << 16) ^ tmp;
+  hash += hash >> 11;
+  return hash;
+}
+DG_HD uint32_t sfh_final(uint32_t hash) {
+  hash ^= hash << 3;
+  hash += hash >> 5;
+  hash ^= hash << 4;
+  hash += hash >> 17;
+  hash ^= hash << 25;
+  hash += hash >> 6;
+  return hash;
+}
+DG_HD uint32_t superfasthash_i32(const int* idx, int n) {
+  if (n <= 0) return 0u;
+  uint32_t h = sfh_init(n);
+  for (int i = 0; i < n; ++i) h = sfh_word(h, (uint32_t)idx[i]);
+  return sfh_final(h);
+}
+
+// Number of samples for a confidence level (reference nsamples, rtools.c:202-225).
+DG_HD int nsamples(int ninl, int ptNum, int samsiz, double conf) {
+  double a = 1.0, b = 1.0;
+  for (int i = 0; i < samsiz; ++i) {
+    a *= ninl - i;
+    b *= ptNum - i;
+  }
+  a = a / b;
+  if (a < kEps) return kMaxSamples;
+  a = 1.0 - a;
+  if (a < kEps) return 1;
+  b = log(1.0 - conf) / log(a);
+  if (b > kMaxSamples) return kMaxSamples;
+  return (int)ceil(b);
+}
+
+// MSAC gain (reference truncQuad, rtools.c:228-236): width (thr*9)/4.
+DG_HD double trunc_quad(double e, double thr) {
+  if (thr == 0) return 0.0;
+  const double w = thr * 9 / 4;
+  if (e >= w) return 0.0;
+  return 1 - (e / w);
+}
+
+}  // namespace dg

@@ -1,0 +1,87 @@
+// hostemu.cpp -- TEST HELPER ONLY.  Compiles the engine headers with plain g++ as a one-thread CTA
+// (tid=0, nt=1, barriers are no-ops) so the ordered-replay control flow can be checked against the
+// reference on a machine without a GPU.  Never loaded by the pydegensac_b200 package.
+#include <stdlib.h>
+#include <string.h>
+#include "../../pydegensac_b200/csrc/engine_f.h"
+#include "../../pydegensac_b200/csrc/engine_h.h"
+#include "../../pydegensac_b200/csrc/workspace.h"
+
+using namespace dg;
+
+struct Emu {
+  Ctx c;
+  Workspace W;
+  BlockScratch sc;
+  unsigned char* slab;
+  double* soa;
+};
+
+static void emu_setup(Emu& E, const double* x1y1, const double* x2y2, int n, int dim, int chunk) {
+  const size_t bytes = workspace_bytes(n, chunk);
+  E.slab = (unsigned char*)calloc(bytes + 256, 1);
+  workspace_carve(E.slab, n, chunk, &E.W, &E.soa);
+  const size_t row = align_up(sizeof(double) * (size_t)n, 128) / sizeof(double);
+  double* x1 = E.soa; double* y1 = E.soa + row; double* x2 = E.soa + 2 * row; double* y2 = E.soa + 3 * row;
+  for (int i = 0; i < n; ++i) {
+    x1[i] = x1y1[(size_t)dim * i]; y1[i] = x1y1[(size_t)dim * i + 1];
+    x2[i] = x2y2[(size_t)dim * i]; y2[i] = x2y2[(size_t)dim * i + 1];
+  }
+  E.c.tid = 0; E.c.nt = 1; E.c.lane = 0; E.c.wid = 0; E.c.nw = 1; E.c.N = n;
+  E.c.x1 = x1; E.c.y1 = y1; E.c.x2 = x2; E.c.y2 = y2;
+  E.c.sc = &E.sc;
+}
+
+extern "C" int emu_find_fundamental(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
+                                    int max_iters, int error_type, int sym_check, double laf_coef, int degen,
+                                    uint64_t seed, int chunk, double* F, unsigned char* mask, int* stats) {
+  if (n < 8 || (dim != 2 && dim != 6)) return -1;
+  if (laf_coef > 0) return -3;
+  Emu E;
+  emu_setup(E, x1y1, x2y2, n, dim, chunk);
+  FParams P;
+  f_thresholds(px_th, sym_check, &P.th, &P.sym_th);
+  P.conf = conf; P.laf_coef = 0; P.max_iters = max_iters; P.metric = error_type; P.degen = degen;
+  P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk;
+  ransac_F_pair(E.c, P, E.W, F, mask, stats);
+  free(E.slab);
+  return 0;
+}
+
+extern "C" int emu_find_homography(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
+                                   int max_iters, int error_type, int sym_check, double laf_coef, uint64_t seed,
+                                   int chunk, double* H, unsigned char* mask, int* stats) {
+  if (n < 4 || (dim != 2 && dim != 6)) return -1;
+  if (laf_coef > 0) return -3;
+  Emu E;
+  emu_setup(E, x1y1, x2y2, n, dim, chunk);
+  HParams P;
+  if (h_thresholds(error_type, px_th, sym_check, &P.th, &P.sym_th)) return -2;
+  P.conf = conf; P.laf_coef = 0; P.max_iters = max_iters; P.metric = error_type;
+  P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk;
+  ransac_H_pair(E.c, P, E.W, H, mask, stats);
+  free(E.slab);
+  return 0;
+}
+
+// ---- leaf exports for known-answer tests against the reference's own leaves ----
+extern "C" int emu_nullspace9(double* M, double* ns) { return nullspace9(M, ns); }
+extern "C" void emu_seven_pt_cubic(const double* A, double* B, double* p) { seven_pt_cubic(A, B, p); }
+extern "C" int emu_cubic_real_roots(const double* po, double* r) { return cubic_real_roots(po, r); }
+extern "C" double emu_f_resid(int metric, const double* F, double x1, double y1, double x2, double y2) { return f_resid(metric, F, x1, y1, x2, y2); }
+extern "C" double emu_h_resid(int metric, const double* H, double x1, double y1, double x2, double y2) {
+  HSym s; h_sym_prepare(H, &s); return h_resid_metric(metric, H, s, x1, y1, x2, y2);
+}
+extern "C" uint32_t emu_hash(const int* idx, int n) { return superfasthash_i32(idx, n); }
+extern "C" int emu_nsamples(int a, int b, int c, double d) { return nsamples(a, b, c, d); }
+extern "C" void emu_min_eigvec9(double* C, double* v) { min_eigvec9(C, v); }
+extern "C" void emu_enforce_rank2(double* F) { enforce_rank2(F); }
+extern "C" void emu_left_null(double* Z, int len, double* q) { left_null_9xk(Z, len, q); }
+extern "C" void emu_minimal_sample(uint64_t seed, uint32_t k, int N, int m, int* sel) {
+  if (m == 7) minimal_sample<7>(seed, k, N, sel); else minimal_sample<4>(seed, k, N, sel);
+}
+extern "C" uint32_t emu_value31(uint64_t seed, uint32_t k, uint32_t j) { return value31(seed, k, j); }
+extern "C" int emu_checksample(const double* F, const double* u7, double th, double* H) {
+  for (int t = 0; t < 5; ++t) if (checksample_triplet(F, u7, t, th, H)) return 1;
+  return 0;
+}
