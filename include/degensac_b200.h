@@ -1,0 +1,98 @@
+/*
+ * degensac_b200.h -- C ABI of the B200-native LO-RANSAC / DEGENSAC engine (libdegensac_b200.so).
+ *
+ * Drop-in boundary for the reference's hot path.  Each entry point states the reference interface it
+ * replaces; conventions (thresholds, metric numbering, model layout) are those of the reference's
+ * binding layer so that a maintainer can rebind `pydegensac.findHomography_/findFundamentalMatrix_`
+ * one-to-one.  Plain pointers and sizes only: no torch / pybind types.
+ *
+ * Common conventions
+ *   x1y1, x2y2 : row-major [n_pairs][n][dim] float64, dim = 2 (x,y) or 6 (x,y,a11,a12,a21,a22); only
+ *                columns 0-1 are correspondences (bindings.cpp:180-197, 391-408).
+ *   px_th, conf, max_iters, error_type, sym_check, laf_coef : exactly the arguments of
+ *                findFundamentalMatrix_/findHomography_ (bindings.cpp:484-503); thresholds are squared /
+ *                scaled inside, as the binding does (bindings.cpp:64-107, 297-318).
+ *   seeds      : one uint64 per pair (NULL -> pair index).  The reference seeds libc rand() from
+ *                time(NULL) (exp_ranF.c:1277, exp_ranH.c:510); here sampling is a counter-based Philox
+ *                stream keyed by (seed, iteration, draw) -> reproducible and order-independent.
+ *   model_out  : [n_pairs][9] float64.  F: row-major, x2^T F x1 = 0 (as the reference returns it).
+ *                H: RAW core output = column-major, maps image 2 -> image 1, i.e. what
+ *                exp_ransacHcustomLAF writes; the Python layer applies inv(H.T) (utils.py:108).
+ *                All-zero model = "no model found" (then the mask is all zero, utils.py:104-107,143-145).
+ *   mask_out   : [n_pairs][n] uint8 (1 = inlier).
+ *   stats_out  : [n_pairs][4] int32 or NULL: {samples drawn, LO runs, plane inliers (F) / 0 (H),
+ *                inlier count of the returned model}  (the reference's data_out[0..1], *Ih, return value).
+ *   return     : 0 ok; <0 error (DGB200_E_*), message via dgb200_last_error().
+ */
+#ifndef DEGENSAC_B200_H
+#define DEGENSAC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGB200_OK 0
+#define DGB200_E_ARG (-1)          /* bad shape: n < 8 (F) / n < 4 (H), dim not 2 or 6 (bindings.cpp:32-47, 267-282) */
+#define DGB200_E_METRIC (-2)       /* unknown error_type (bindings.cpp:10-17) */
+#define DGB200_E_UNSUPPORTED (-3)  /* laf_coef > 0: LAF-consistency gate not built yet */
+#define DGB200_E_CUDA (-10)        /* no device / CUDA runtime failure: the engine has no CPU fallback */
+
+/* error_type numbering of the reference (bindings.cpp:10-17) */
+#define DGB200_F_SAMPSON 0
+#define DGB200_F_SYMM_EPIPOLAR 1
+#define DGB200_H_SAMPSON 0
+#define DGB200_H_SYMM_SQ_MAX 1
+#define DGB200_H_SYMM_MAX 2
+#define DGB200_H_SYMM_SQ_SUM 3
+#define DGB200_H_SYMM_SUM 4
+
+/* Replaces exp_ransacFcustomLAF (exp_ranF.h:69-74, exp_ranF.c:1244) as called by findFundamentalMatrix_
+ * (bindings.cpp:253-467), batched over independent image pairs.  HOST buffers; synchronous (copies in,
+ * runs the wave/replay kernel, copies out). */
+int dgb200_find_fundamental_batch(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim,
+                                  double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                  double laf_coef, int degen_check, const uint64_t* seeds,
+                                  double* F_out, uint8_t* mask_out, int32_t* stats_out);
+
+/* Replaces exp_ransacHcustomLAF (exp_ranH.h:27-33, exp_ranH.c:470; iter_type 4, oriented constraint on,
+ * inlLimit 0) as called by findHomography_ (bindings.cpp:19-251).  HOST buffers; synchronous. */
+int dgb200_find_homography_batch(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim,
+                                 double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                 double laf_coef, const uint64_t* seeds,
+                                 double* H_out, uint8_t* mask_out, int32_t* stats_out);
+
+/* Same two paths with DEVICE pointers (inputs already resident in HBM, outputs left in HBM) on a CUDA
+ * stream (cudaStream_t passed as void*; NULL = default stream).  Asynchronous: returns after enqueueing. */
+int dgb200_find_fundamental_batch_dev(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
+                                      double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                      double laf_coef, int degen_check, const uint64_t* d_seeds,
+                                      double* d_F_out, uint8_t* d_mask_out, int32_t* d_stats_out, void* stream);
+int dgb200_find_homography_batch_dev(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
+                                     double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                     double laf_coef, const uint64_t* d_seeds,
+                                     double* d_H_out, uint8_t* d_mask_out, int32_t* d_stats_out, void* stream);
+
+/* One pair (what one findFundamentalMatrix_/findHomography_ call does): batch of 1 with one seed. */
+int dgb200_find_fundamental(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
+                            int max_iters, int error_type, int sym_check, double laf_coef, int degen_check,
+                            uint64_t seed, double* F_out, uint8_t* mask_out, int32_t* stats_out);
+int dgb200_find_homography(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
+                           int max_iters, int error_type, int sym_check, double laf_coef,
+                           uint64_t seed, double* H_out, uint8_t* mask_out, int32_t* stats_out);
+
+/* Housekeeping */
+int dgb200_version(void);              /* ABI version */
+int dgb200_device_count(void);         /* CUDA devices visible (0 or <0: the engine cannot run) */
+int dgb200_set_device(int device);     /* device used by subsequent calls of this thread's process */
+const char* dgb200_last_error(void);   /* last error message (static storage) */
+long long dgb200_kernel_launches(void);/* RANSAC kernels launched so far by this process */
+double dgb200_last_kernel_ms(void);    /* device time of the most recent HOST-buffer call's kernel (CUDA events) */
+void dgb200_release(void);             /* free cached device buffers */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEGENSAC_B200_H */

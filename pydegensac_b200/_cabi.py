@@ -1,0 +1,131 @@
+"""ctypes binding of the C ABI (include/degensac_b200.h) -- used for the batched entry points.
+
+The library is the product: if libdegensac_b200.so is missing or no CUDA device is visible, calls raise.
+There is no CPU fallback anywhere in this package.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libdegensac_b200.so")
+_lib = None
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIBPATH):
+            raise EngineUnavailable(
+                "pydegensac_b200: %s is missing - build it with `python -m pydegensac_b200.build` "
+                "(the engine is CUDA-only; there is no CPU fallback)" % _LIBPATH)
+        L = ctypes.CDLL(_LIBPATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        u8 = ctypes.POINTER(ctypes.c_uint8)
+        i32 = ctypes.POINTER(ctypes.c_int32)
+        u64 = ctypes.POINTER(ctypes.c_uint64)
+        ci, cd = ctypes.c_int, ctypes.c_double
+        L.dgb200_find_fundamental_batch.argtypes = [dp, dp, ci, ci, ci, cd, cd, ci, ci, ci, cd, ci, u64, dp, u8, i32]
+        L.dgb200_find_homography_batch.argtypes = [dp, dp, ci, ci, ci, cd, cd, ci, ci, ci, cd, u64, dp, u8, i32]
+        vp = ctypes.c_void_p
+        L.dgb200_find_fundamental_batch_dev.argtypes = [vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, ci, vp, vp, vp, vp, vp]
+        L.dgb200_find_homography_batch_dev.argtypes = [vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, vp, vp, vp, vp, vp]
+        L.dgb200_last_error.restype = ctypes.c_char_p
+        L.dgb200_kernel_launches.restype = ctypes.c_longlong
+        L.dgb200_last_kernel_ms.restype = ctypes.c_double
+        _lib = L
+    return _lib
+
+
+def _raise(rc):
+    msg = lib().dgb200_last_error().decode()
+    if rc in (-1, -2, -3):
+        raise ValueError(msg)
+    raise EngineUnavailable("degensac_b200: " + msg)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def _prep(pts1, pts2):
+    p1 = np.ascontiguousarray(pts1, dtype=np.float64)
+    p2 = np.ascontiguousarray(pts2, dtype=np.float64)
+    if p1.ndim == 2:
+        p1, p2 = p1[None], p2[None]
+    if p1.ndim != 3 or p1.shape != p2.shape:
+        raise ValueError("expected two arrays of shape [P,N,2] or [P,N,6] with equal shapes")
+    return p1, p2
+
+
+def _seeds(seeds, P):
+    if seeds is None:
+        return None
+    s = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.uint64), (P,)))
+    return s
+
+
+def fundamental_batch(pts1, pts2, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check, seeds):
+    p1, p2 = _prep(pts1, pts2)
+    P, N, dim = p1.shape
+    F = np.zeros((P, 3, 3), dtype=np.float64)
+    mask = np.zeros((P, N), dtype=np.uint8)
+    stats = np.zeros((P, 4), dtype=np.int32)
+    s = _seeds(seeds, P)
+    rc = lib().dgb200_find_fundamental_batch(_p(p1, ctypes.c_double), _p(p2, ctypes.c_double), P, N, dim,
+                                             float(px_th), float(conf), int(max_iters), int(error_type),
+                                             int(bool(sym_check)), float(laf_coef), int(bool(degen_check)),
+                                             _p(s, ctypes.c_uint64) if s is not None else None,
+                                             _p(F, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32))
+    if rc != 0:
+        _raise(rc)
+    return F, mask.astype(bool), stats
+
+
+def homography_batch(pts1, pts2, px_th, conf, max_iters, error_type, sym_check, laf_coef, seeds):
+    p1, p2 = _prep(pts1, pts2)
+    P, N, dim = p1.shape
+    H = np.zeros((P, 3, 3), dtype=np.float64)
+    mask = np.zeros((P, N), dtype=np.uint8)
+    stats = np.zeros((P, 4), dtype=np.int32)
+    s = _seeds(seeds, P)
+    rc = lib().dgb200_find_homography_batch(_p(p1, ctypes.c_double), _p(p2, ctypes.c_double), P, N, dim,
+                                            float(px_th), float(conf), int(max_iters), int(error_type),
+                                            int(bool(sym_check)), float(laf_coef),
+                                            _p(s, ctypes.c_uint64) if s is not None else None,
+                                            _p(H, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32))
+    if rc != 0:
+        _raise(rc)
+    return H, mask.astype(bool), stats
+
+
+def fundamental_batch_dev(d_p1, d_p2, P, N, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check,
+                          d_seeds, d_F, d_mask, d_stats, stream=0):
+    """Device-pointer flavour: all d_* are integer device addresses (e.g. torch.Tensor.data_ptr())."""
+    rc = lib().dgb200_find_fundamental_batch_dev(d_p1, d_p2, P, N, dim, float(px_th), float(conf), int(max_iters),
+                                                 int(error_type), int(bool(sym_check)), float(laf_coef),
+                                                 int(bool(degen_check)), d_seeds, d_F, d_mask, d_stats, stream)
+    if rc != 0:
+        _raise(rc)
+
+
+def homography_batch_dev(d_p1, d_p2, P, N, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, d_seeds,
+                         d_H, d_mask, d_stats, stream=0):
+    rc = lib().dgb200_find_homography_batch_dev(d_p1, d_p2, P, N, dim, float(px_th), float(conf), int(max_iters),
+                                                int(error_type), int(bool(sym_check)), float(laf_coef), d_seeds, d_H,
+                                                d_mask, d_stats, stream)
+    if rc != 0:
+        _raise(rc)
+
+
+def kernel_launches():
+    return int(lib().dgb200_kernel_launches())
+
+
+def last_kernel_ms():
+    return float(lib().dgb200_last_kernel_ms())

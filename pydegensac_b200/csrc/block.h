@@ -91,7 +91,7 @@ DG_ENG inline int blk_excl_scan_i(const Ctx& c, int v, int* total) {
   return base + incl - v;
 }
 // k-wide vector sum (k <= kVecRed); result in c.sc->vec_out[0..k), visible to all threads on return.
-DG_ENG inline void blk_sum_vec(const Ctx& c, double* v, int k) {
+DG_ENGN void blk_sum_vec(const Ctx& c, double* v, int k) {
   DG_SYNC();
   for (int i = 0; i < k; ++i) {
     const double s = warp_sum(v[i]);
@@ -115,7 +115,7 @@ DG_ENG inline void bc_fetch(const Ctx& c, double* dst, int n) {
 // MSAC score + ascending inlier index list of a residual row (reference inlidxs, rtools.c:160-171):
 // J = sum truncQuad(err, th), list = {i : err[i] <= th}.  Threads own contiguous index segments so the
 // list comes out ordered after one block scan.
-DG_ENG inline Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list) {
+DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list) {
   const int per = (c.N + c.nt - 1) / c.nt;
   const int beg = c.tid * per;
   const int end = (beg + per < c.N) ? beg + per : c.N;

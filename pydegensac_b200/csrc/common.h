@@ -13,10 +13,14 @@
 
 #if defined(__CUDACC__)
 #define DG_HD __host__ __device__ __forceinline__
+#define DG_HDN __host__ __device__ __noinline__ inline   /* heavy leaf: one copy, keeps ptxas time sane */
 #define DG_ENG __device__
+#define DG_ENGN __device__ __noinline__ inline
 #else
 #define DG_HD inline
+#define DG_HDN inline
 #define DG_ENG
+#define DG_ENGN inline
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -24,9 +24,9 @@ namespace dg {
 // Homography compatible with F through 3 correspondences (Hartley & Zisserman p.318; reference Hdetect,
 // DegUtils.c:93-161).  u7 holds the sample as 7 x (x1,y1,x2,y2); H is column-major, image2 -> image1.
 // ------------------------------------------------------------------------------------------------
-DG_HD void h_from_F_3pts(const double* F, const double* u7, const int* tri, double* H) {
+DG_HDN void h_from_F_3pts(const double* F, const double* u7, const int* tri, double* H) {
   double ec[3];
-  right_null3(F, ec);  // F ec = 0 : third right singular vector of the row-major F
+  gkr_third_right_vector3(F, ec);  // column 2 of CCMATH's V (usually, not always, F ec = 0)
   const double Ex[9] = {0, -ec[2], ec[1], ec[2], 0, -ec[0], -ec[1], ec[0], 0};
   double A[9];  // A = [ec]x * F^T
   for (int i = 0; i < 3; ++i)
@@ -67,7 +67,7 @@ DG_HD void h_from_F_3pts(const double* F, const double* u7, const int* tri, doub
 }
 
 // One-thread normalised DLT on a handful of points given explicitly (the 5-point refit of checksample).
-DG_HD void h_fit_small(const double* u7, const int* idx, int len, double* h) {
+DG_HDN void h_fit_small(const double* u7, const int* idx, int len, double* h) {
   double A1[3] = {0, 0, 0}, A2[3] = {0, 0, 0};
   for (int j = 0; j < len; ++j) {
     const double* p = u7 + 4 * idx[j];
@@ -109,7 +109,7 @@ DG_HD void h_fit_small(const double* u7, const int* idx, int len, double* h) {
 }
 
 // One triplet of the degeneracy test (body of the loop in checksample, DegUtils.c:55-80).
-DG_HD bool checksample_triplet(const double* F, const double* u7, int t, double th, double* H) {
+DG_HDN bool checksample_triplet(const double* F, const double* u7, int t, double th, double* H) {
   const int TRI[5][3] = {{0, 1, 2}, {3, 4, 5}, {0, 1, 6}, {3, 4, 6}, {2, 5, 6}};
   h_from_F_3pts(F, u7, TRI[t], H);
   double Ds[7];
@@ -133,7 +133,7 @@ DG_HD bool checksample_triplet(const double* F, const double* u7, int t, double 
 
 // checksample: 5 warps test the 5 triplets concurrently; the first successful triplet (reference order)
 // provides H.  Returns the verdict to every thread, H in every thread's copy.
-DG_ENG inline bool blk_checksample(const Ctx& c, const double* F, const double* u7, double th, double* H) {
+DG_ENGN bool blk_checksample(const Ctx& c, const double* F, const double* u7, double th, double* H) {
   DG_SYNC();
   const int par = (c.nw >= 5) ? 5 : 1;
   if (c.lane == 0 && c.wid < par) {
@@ -161,7 +161,7 @@ DG_ENG inline bool blk_checksample(const Ctx& c, const double* F, const double* 
 // Sampson metric, threshold 16*th, inlLimit = 10.  Uses its own four residual rows (W.dtmp[0..3]).
 // Writes the plane-inlier mask, returns its population.
 // ------------------------------------------------------------------------------------------------
-DG_ENG inline Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** rows, int* inl, double th, double ths,
+DG_ENGN Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** rows, int* inl, double th, double ths,
                                  double* Hio, unsigned inlLimit, DrawCursor& cur) {
   int d = e[1];
   double h[9];
@@ -207,7 +207,7 @@ DG_ENG inline Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** ro
   return maxS;
 }
 
-DG_ENG inline unsigned blk_inner_H(const Ctx& c, Workspace& W, double* H, double th, unsigned inlLimit,
+DG_ENGN unsigned blk_inner_H(const Ctx& c, Workspace& W, double* H, double th, unsigned inlLimit,
                                    unsigned char* mask, DrawCursor& cur) {
   double* rows[4] = {W.dtmp[0], W.dtmp[1], W.dtmp[2], W.dtmp[3]};
   int e[5] = {0, 1, 2, 3, 3};
@@ -251,7 +251,7 @@ DG_ENG inline unsigned blk_inner_H(const Ctx& c, Workspace& W, double* H, double
 
 // ordered compaction of {i : flag(i)} into list; returns count
 template <class Pred>
-DG_ENG inline int blk_compact(const Ctx& c, int n, int* list, Pred pred) {
+DG_ENGN int blk_compact(const Ctx& c, int n, int* list, Pred pred) {
   const int per = (n + c.nt - 1) / c.nt;
   const int beg = c.tid * per;
   const int end = (beg + per < n) ? beg + per : n;
@@ -270,7 +270,7 @@ DG_ENG inline int blk_compact(const Ctx& c, int n, int* list, Pred pred) {
 // Iterated LSQ of F on all inliers with shrinking strict threshold (reference u2Fit, DegUtils.c:635-690).
 // F in/out; mask out; returns population.  Ds row = W.dtmp[5], list = W.itmp[3].
 // ------------------------------------------------------------------------------------------------
-DG_ENG inline unsigned blk_u2Fit(const Ctx& c, Workspace& W, double* F, unsigned char* mask, double th, double ths,
+DG_ENGN unsigned blk_u2Fit(const Ctx& c, Workspace& W, double* F, unsigned char* mask, double th, double ths,
                                  unsigned iters) {
   const double dth = (ths - th) / (iters - 1);
   double* Ds = W.dtmp[5];
@@ -308,7 +308,7 @@ DG_ENG inline unsigned blk_u2Fit(const Ctx& c, Workspace& W, double* F, unsigned
 // uH list (plane inliers, nH), uO list (off-plane support, nO), 15 reps of 6 + 4 points.
 // Output: F (9) and inlier mask `inl` (N).  Scratch masks: W.btmp[2] (v).  Returns nothing (max_i unused).
 // ------------------------------------------------------------------------------------------------
-DG_ENG inline void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, const int* uO, int nO, double th,
+DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, const int* uO, int nO, double th,
                                 double* F, unsigned char* inl, DrawCursor& cur) {
   unsigned char* v = W.btmp[2];
   double* Ds = W.dtmp[5];
@@ -409,7 +409,7 @@ DG_HD void f_from_plane_parallax(const double* H, double ax1, double ay1, double
 // Plane-and-parallax: reference rFtH (DegUtils.c:254-444).  hinl = plane-inlier mask (from innerH).
 // Returns max_i; F written only when a better model was found (as in the reference).
 // ------------------------------------------------------------------------------------------------
-DG_ENG inline unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl, double th, const double* H,
+DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl, double th, const double* H,
                                 double* F, DrawCursor& cur) {
   double* Ds = W.dtmp[4];
   unsigned char* nhinl = W.btmp[1];

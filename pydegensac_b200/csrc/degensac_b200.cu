@@ -1,0 +1,345 @@
+// degensac_b200.cu -- sm_100a kernel + C ABI (include/degensac_b200.h) of the LO-RANSAC / DEGENSAC engine.
+//
+// One persistent CTA processes one image pair at a time (pairs are claimed from an atomic work counter):
+//   * the pair's correspondences are read once from HBM (coalesced 16-byte loads of the [n][dim] rows)
+//     and de-interleaved into a structure-of-arrays tile in shared memory (4 x n doubles);
+//   * engine_f.h / engine_h.h run the speculative hypothesis WAVES (thread per minimal sample, warp per
+//     scored model) and the ordered REPLAY (LO, DEGENSAC, termination) entirely on that tile;
+//   * residual rows, index lists, the hypothesis queue and the LO hash table live in a per-CTA slab of
+//     global memory that stays L2 resident.
+// All arithmetic on the path is FP64 compiled with -fmad=false so residuals, scores and solves round
+// exactly like the reference's x86-64 (no-FMA) build; there is no tensor-core work and no CPU fallback.
+#include <cuda_runtime.h>
+#include <mutex>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/degensac_b200.h"
+#include "engine_f.h"
+#include "engine_h.h"
+#include "workspace.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kChunk = 512;
+
+struct BatchArgs {
+  const double* x1y1;
+  const double* x2y2;
+  int n_pairs, n, dim;
+  double px_th, conf, laf_coef;
+  int max_iters, metric, sym_check, degen;
+  const unsigned long long* seeds;
+  double* model_out;
+  unsigned char* mask_out;
+  int* stats_out;
+  unsigned char* workspace;
+  size_t ws_stride;
+  int chunk;
+  int* work_counter;
+  int pts_in_smem;
+};
+
+template <int KIND>  // 0: fundamental matrix, 1: homography
+__global__ void __launch_bounds__(kThreads, 2) ransac_pairs_kernel(BatchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_pair;
+  dg::BlockScratch* sc = reinterpret_cast<dg::BlockScratch*>(smem_raw);
+  const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128);
+  const int n = a.n;
+  dg::Workspace W;
+  double* soa_global;
+  dg::workspace_carve(a.workspace + (size_t)blockIdx.x * a.ws_stride, n, a.chunk, &W, &soa_global);
+  const size_t row = dg::align_up(sizeof(double) * (size_t)n, 128) / sizeof(double);
+  double* soa = a.pts_in_smem ? reinterpret_cast<double*>(smem_raw + sc_bytes) : soa_global;
+
+  dg::Ctx c;
+  c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5;
+  c.N = n;
+  c.x1 = soa; c.y1 = soa + row; c.x2 = soa + 2 * row; c.y2 = soa + 3 * row;
+  c.sc = sc;
+
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_pair = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int p = s_pair;
+    if (p >= a.n_pairs) break;
+    // ---- stage the pair: HBM -> SoA tile
+    const double* g1 = a.x1y1 + (size_t)p * n * a.dim;
+    const double* g2 = a.x2y2 + (size_t)p * n * a.dim;
+    if (a.dim == 2) {
+      const double2* v1 = reinterpret_cast<const double2*>(g1);
+      const double2* v2 = reinterpret_cast<const double2*>(g2);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 q1 = __ldg(v1 + i), q2 = __ldg(v2 + i);
+        soa[i] = q1.x; soa[row + i] = q1.y; soa[2 * row + i] = q2.x; soa[3 * row + i] = q2.y;
+      }
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        soa[i] = g1[(size_t)i * a.dim]; soa[row + i] = g1[(size_t)i * a.dim + 1];
+        soa[2 * row + i] = g2[(size_t)i * a.dim]; soa[3 * row + i] = g2[(size_t)i * a.dim + 1];
+      }
+    }
+    __syncthreads();
+    const unsigned long long seed = a.seeds ? a.seeds[p] : (unsigned long long)p;
+    double* model = a.model_out + (size_t)p * 9;
+    unsigned char* mask = a.mask_out + (size_t)p * n;
+    int local_stats[4];
+    __shared__ int s_stats[4];
+    if (KIND == 0) {
+      dg::FParams P;
+      dg::f_thresholds(a.px_th, a.sym_check, &P.th, &P.sym_th);
+      P.conf = a.conf; P.laf_coef = 0.0; P.max_iters = a.max_iters; P.metric = a.metric; P.degen = a.degen;
+      P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = a.chunk;
+      dg::ransac_F_pair(c, P, W, model, mask, s_stats);
+    } else {
+      dg::HParams P;
+      dg::h_thresholds(a.metric, a.px_th, a.sym_check, &P.th, &P.sym_th);
+      P.conf = a.conf; P.laf_coef = 0.0; P.max_iters = a.max_iters; P.metric = a.metric;
+      P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = a.chunk;
+      dg::ransac_H_pair(c, P, W, model, mask, s_stats);
+    }
+    __syncthreads();
+    // "no model" convention of the Python layer (utils.py:104-107, 143-145): zero model -> empty mask
+    double asum = 0.0;
+    for (int i = 0; i < 9; ++i) asum += fabs(model[i]);
+    if (asum == 0.0)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) mask[i] = 0;
+    if (a.stats_out && threadIdx.x < 4) a.stats_out[(size_t)p * 4 + threadIdx.x] = s_stats[threadIdx.x];
+    (void)local_stats;
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+struct Cache {
+  int device = -1;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  unsigned char* ws = nullptr; size_t ws_bytes = 0;
+  int* counter = nullptr;
+  unsigned char* io = nullptr; size_t io_bytes = 0;   // staging for the host-buffer flavour
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+std::mutex g_mu;
+Cache g_c;
+char g_err[512] = "";
+long long g_launches = 0;
+double g_last_ms = 0.0;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(g_err, sizeof(g_err), "%s", what);
+  return code;
+}
+#define CU(call)                                                     \
+  do {                                                               \
+    cudaError_t e__ = (call);                                        \
+    if (e__ != cudaSuccess) return fail(DGB200_E_CUDA, #call, e__);  \
+  } while (0)
+
+int ensure_device() {
+  if (g_c.device >= 0) { CU(cudaSetDevice(g_c.device)); return 0; }
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt <= 0) return fail(DGB200_E_CUDA, "no CUDA device: the B200 engine has no CPU fallback", e);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  g_c.device = dev;
+  g_c.sm_count = prop.multiProcessorCount;
+  g_c.smem_optin = prop.sharedMemPerBlockOptin;
+  CU(cudaEventCreate(&g_c.ev0));
+  CU(cudaEventCreate(&g_c.ev1));
+  return 0;
+}
+
+template <int KIND>
+int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, double px_th, double conf, int max_iters,
+           int metric, int sym_check, int degen, const unsigned long long* d_seeds, double* d_model,
+           unsigned char* d_mask, int* d_stats, cudaStream_t st) {
+  BatchArgs a;
+  a.x1y1 = d1; a.x2y2 = d2; a.n_pairs = n_pairs; a.n = n; a.dim = dim;
+  a.px_th = px_th; a.conf = conf; a.laf_coef = 0.0; a.max_iters = max_iters; a.metric = metric;
+  a.sym_check = sym_check; a.degen = degen; a.seeds = d_seeds;
+  a.model_out = d_model; a.mask_out = d_mask; a.stats_out = d_stats;
+  a.chunk = kChunk;
+  const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128);
+  const size_t tile = dg::align_up(sizeof(double) * (size_t)n, 128) * 4;
+  size_t smem = sc_bytes + tile;
+  a.pts_in_smem = 1;
+  if (smem > g_c.smem_optin) { smem = sc_bytes; a.pts_in_smem = 0; }
+  auto kern = ransac_pairs_kernel<KIND>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) return fail(DGB200_E_CUDA, "kernel does not fit on an SM");
+  int grid = g_c.sm_count * per_sm;     // persistent CTAs: a whole number of CTAs per SM
+  if (grid > n_pairs) grid = n_pairs;
+  a.ws_stride = dg::align_up(dg::workspace_bytes(n, kChunk), 256);
+  const size_t need = a.ws_stride * (size_t)grid;
+  if (need > g_c.ws_bytes) {
+    if (g_c.ws) cudaFree(g_c.ws);
+    g_c.ws = nullptr; g_c.ws_bytes = 0;
+    CU(cudaMalloc(&g_c.ws, need));
+    g_c.ws_bytes = need;
+  }
+  if (!g_c.counter) CU(cudaMalloc(&g_c.counter, sizeof(int)));
+  a.workspace = g_c.ws;
+  a.work_counter = g_c.counter;
+  CU(cudaMemsetAsync(g_c.counter, 0, sizeof(int), st));
+  kern<<<grid, kThreads, smem, st>>>(a);
+  CU(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int check_args(int kind, const void* p1, const void* p2, int n_pairs, int n, int dim, int metric, double laf_coef,
+               const void* m, const void* k) {
+  if (!p1 || !p2 || !m || !k) return fail(DGB200_E_ARG, "null buffer");
+  if (n_pairs < 1) return fail(DGB200_E_ARG, "n_pairs must be >= 1");
+  if (dim != 2 && dim != 6) return fail(DGB200_E_ARG, "x1y1 should be an array with dims [n,2], [n,6]");
+  if (kind == 0 && n < 8) return fail(DGB200_E_ARG, "x1y1 should be an array with dims [n,2], n>=8");
+  if (kind == 1 && n < 4) return fail(DGB200_E_ARG, "x1y1 should be an array with dims [n,2], n>=4");
+  if (kind == 0 && (metric < 0 || metric > 1)) return fail(DGB200_E_METRIC, "unknown fundamental-matrix error_type");
+  if (kind == 1 && (metric < 0 || metric > 4)) return fail(DGB200_E_METRIC, "unknown homography error_type");
+  if (laf_coef > 0) return fail(DGB200_E_UNSUPPORTED, "laf_coef > 0 (LAF consistency gate) is not implemented yet");
+  return 0;
+}
+
+template <int KIND>
+int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim, double px_th, double conf,
+             int max_iters, int metric, int sym_check, double laf_coef, int degen, const uint64_t* seeds,
+             double* model_out, uint8_t* mask_out, int32_t* stats_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = check_args(KIND, x1y1, x2y2, n_pairs, n, dim, metric, laf_coef, model_out, mask_out);
+  if (rc) return rc;
+  rc = ensure_device();
+  if (rc) return rc;
+  const size_t in_b = dg::align_up(sizeof(double) * (size_t)n_pairs * n * dim, 256);
+  const size_t seed_b = dg::align_up(sizeof(uint64_t) * (size_t)n_pairs, 256);
+  const size_t model_b = dg::align_up(sizeof(double) * 9 * (size_t)n_pairs, 256);
+  const size_t mask_b = dg::align_up((size_t)n_pairs * n, 256);
+  const size_t stats_b = dg::align_up(sizeof(int) * 4 * (size_t)n_pairs, 256);
+  const size_t need = 2 * in_b + seed_b + model_b + mask_b + stats_b;
+  if (need > g_c.io_bytes) {
+    if (g_c.io) cudaFree(g_c.io);
+    g_c.io = nullptr; g_c.io_bytes = 0;
+    CU(cudaMalloc(&g_c.io, need));
+    g_c.io_bytes = need;
+  }
+  unsigned char* p = g_c.io;
+  double* d1 = (double*)p; p += in_b;
+  double* d2 = (double*)p; p += in_b;
+  unsigned long long* dseed = (unsigned long long*)p; p += seed_b;
+  double* dmodel = (double*)p; p += model_b;
+  unsigned char* dmask = p; p += mask_b;
+  int* dstats = (int*)p;
+  cudaStream_t st = 0;
+  CU(cudaMemcpyAsync(d1, x1y1, sizeof(double) * (size_t)n_pairs * n * dim, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d2, x2y2, sizeof(double) * (size_t)n_pairs * n * dim, cudaMemcpyHostToDevice, st));
+  if (seeds) CU(cudaMemcpyAsync(dseed, seeds, sizeof(uint64_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(g_c.ev0, st));
+  rc = launch<KIND>(d1, d2, n_pairs, n, dim, px_th, conf, max_iters, metric, sym_check, degen, seeds ? dseed : nullptr,
+                    dmodel, dmask, dstats, st);
+  if (rc) return rc;
+  CU(cudaEventRecord(g_c.ev1, st));
+  CU(cudaMemcpyAsync(model_out, dmodel, sizeof(double) * 9 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(mask_out, dmask, (size_t)n_pairs * n, cudaMemcpyDeviceToHost, st));
+  if (stats_out) CU(cudaMemcpyAsync(stats_out, dstats, sizeof(int) * 4 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, g_c.ev0, g_c.ev1));
+  g_last_ms = ms;
+  return 0;
+}
+
+template <int KIND>
+int run_dev(const double* d1, const double* d2, int n_pairs, int n, int dim, double px_th, double conf, int max_iters,
+            int metric, int sym_check, double laf_coef, int degen, const uint64_t* d_seeds, double* d_model,
+            uint8_t* d_mask, int32_t* d_stats, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = check_args(KIND, d1, d2, n_pairs, n, dim, metric, laf_coef, d_model, d_mask);
+  if (rc) return rc;
+  rc = ensure_device();
+  if (rc) return rc;
+  return launch<KIND>(d1, d2, n_pairs, n, dim, px_th, conf, max_iters, metric, sym_check, degen,
+                      (const unsigned long long*)d_seeds, d_model, d_mask, d_stats, (cudaStream_t)stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dgb200_find_fundamental_batch(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim, double px_th,
+                                  double conf, int max_iters, int error_type, int sym_check, double laf_coef,
+                                  int degen_check, const uint64_t* seeds, double* F_out, uint8_t* mask_out,
+                                  int32_t* stats_out) {
+  return run_host<0>(x1y1, x2y2, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check,
+                     seeds, F_out, mask_out, stats_out);
+}
+int dgb200_find_homography_batch(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim, double px_th,
+                                 double conf, int max_iters, int error_type, int sym_check, double laf_coef,
+                                 const uint64_t* seeds, double* H_out, uint8_t* mask_out, int32_t* stats_out) {
+  return run_host<1>(x1y1, x2y2, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0, seeds,
+                     H_out, mask_out, stats_out);
+}
+int dgb200_find_fundamental_batch_dev(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
+                                      double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                      double laf_coef, int degen_check, const uint64_t* d_seeds, double* d_F_out,
+                                      uint8_t* d_mask_out, int32_t* d_stats_out, void* stream) {
+  return run_dev<0>(d_x1y1, d_x2y2, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef,
+                    degen_check, d_seeds, d_F_out, d_mask_out, d_stats_out, stream);
+}
+int dgb200_find_homography_batch_dev(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
+                                     double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                     double laf_coef, const uint64_t* d_seeds, double* d_H_out, uint8_t* d_mask_out,
+                                     int32_t* d_stats_out, void* stream) {
+  return run_dev<1>(d_x1y1, d_x2y2, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0,
+                    d_seeds, d_H_out, d_mask_out, d_stats_out, stream);
+}
+int dgb200_find_fundamental(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
+                            int max_iters, int error_type, int sym_check, double laf_coef, int degen_check,
+                            uint64_t seed, double* F_out, uint8_t* mask_out, int32_t* stats_out) {
+  return run_host<0>(x1y1, x2y2, 1, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check, &seed,
+                     F_out, mask_out, stats_out);
+}
+int dgb200_find_homography(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
+                           int max_iters, int error_type, int sym_check, double laf_coef, uint64_t seed, double* H_out,
+                           uint8_t* mask_out, int32_t* stats_out) {
+  return run_host<1>(x1y1, x2y2, 1, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0, &seed, H_out,
+                     mask_out, stats_out);
+}
+
+int dgb200_version(void) { return 1; }
+int dgb200_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) return -1;
+  return cnt;
+}
+int dgb200_set_device(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_c.device >= 0 && g_c.device != device) {
+    if (g_c.ws) cudaFree(g_c.ws);
+    if (g_c.io) cudaFree(g_c.io);
+    if (g_c.counter) cudaFree(g_c.counter);
+    g_c = Cache();
+  }
+  CU(cudaSetDevice(device));
+  return 0;
+}
+const char* dgb200_last_error(void) { return g_err; }
+long long dgb200_kernel_launches(void) { return g_launches; }
+double dgb200_last_kernel_ms(void) { return g_last_ms; }
+void dgb200_release(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_c.device >= 0) cudaSetDevice(g_c.device);
+  if (g_c.ws) cudaFree(g_c.ws);
+  if (g_c.io) cudaFree(g_c.io);
+  if (g_c.counter) cudaFree(g_c.counter);
+  g_c.ws = nullptr; g_c.io = nullptr; g_c.counter = nullptr; g_c.ws_bytes = 0; g_c.io_bytes = 0;
+}
+
+}  // extern "C"

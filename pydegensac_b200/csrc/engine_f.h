@@ -34,7 +34,7 @@ namespace dg {
 // The reference de-duplicates LO inlier sets with SuperFastHash + a 64-bucket chained table
 // (hash.c:49-96, exp_ranF.c:675-686).  Only "(hash,len) seen under this iterID / another iterID /
 // never" matters, so a flat list is equivalent.  Returns true when the refinement must abort.
-DG_ENG inline bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
+DG_ENGN bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
   DG_SYNC();
   if (c.tid == 0) {
     const uint32_t h = superfasthash_i32(list, n);
@@ -61,7 +61,7 @@ DG_ENG inline bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, 
 // e[] are the physical ids behind the reference's errs[] pointers; e[4] holds the residual row of the
 // starting model.  With the binding's inlLimit=0 every fit uses a random 8-subset.
 // ---------------------------------------------------------------------------------------------
-DG_ENG inline Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int* e, int* inl, double th,
+DG_ENGN Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int* e, int* inl, double th,
                               double ths, double* Fio, int iterID, DrawCursor& cur, HashTab& ht) {
   int d = e[1];
   double f[9];
@@ -109,7 +109,7 @@ DG_ENG inline Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int*
 }
 
 // Inner RANSAC of the LO step (reference exp_inFranicustom, exp_ranF.c:745-806).
-DG_ENG inline Score lo_inner_F(const Ctx& c, const FParams& P, Workspace& W, int* e, int* inliers, int ninl,
+DG_ENGN Score lo_inner_F(const Ctx& c, const FParams& P, Workspace& W, int* e, int* inliers, int ninl,
                                double th, double* Fout, int& iterID, DrawCursor& cur, HashTab& ht) {
   Score S, maxS = make_score();
   if (ninl < 16) return maxS;
@@ -151,7 +151,7 @@ struct FState {
 
 // "LSQ before LO" + LO + acceptance (exp_ranF.c:1501-1577 in the loop, :1630-1696 post-loop).
 // src_row: residual row the LSQ support is taken from (errs[4] in the loop, errorsBest post-loop).
-DG_ENG inline bool run_lo_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, const double* src_row) {
+DG_ENGN bool run_lo_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, const double* src_row) {
   double f[9];
   bool new_max = false;
   ++st.iter_cnt;
@@ -183,7 +183,7 @@ DG_ENG inline bool run_lo_F(const Ctx& c, const FParams& P, Workspace& W, FState
 // their indices into W.cand sorted by (iteration, root).  valid_itersam reports whether iteration
 // ITER_SAM produced a two-dimensional null space (needed for the forced-LO rule).
 // ---------------------------------------------------------------------------------------------
-DG_ENG inline int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int kend, double T, bool passall,
+DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int kend, double T, bool passall,
                          bool* valid_itersam) {
   DG_SYNC();
   if (c.tid == 0) { c.sc->counter[0] = 0; c.sc->counter[1] = 0; c.sc->counter[2] = 0; }
@@ -276,7 +276,7 @@ DG_ENG inline int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg,
 
 // Final inlier mask (exp_ranF.c:1699-1723) incl. the reference's indexing quirk in the symmetric prune
 // (it clears mask[j] for the j-th LIST POSITION instead of mask[inliers[j]]).
-DG_ENG inline void final_mask_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, unsigned char* mask) {
+DG_ENGN void final_mask_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, unsigned char* mask) {
   const double* d = W.err[st.e[3]];
   for (int j = c.tid; j < c.N; j += c.nt) mask[j] = (d[j] <= P.th) ? 1 : 0;
   DG_SYNC();
@@ -294,7 +294,7 @@ DG_ENG inline void final_mask_F(const Ctx& c, const FParams& P, Workspace& W, FS
 // REPLAY of one iteration (the body of the reference's while loop, exp_ranF.c:1334-1578) restricted to
 // the models that survived the wave (`cnt` entries of W.pass starting at `pos`, ascending root order).
 // ---------------------------------------------------------------------------------------------
-DG_ENG inline void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, int k, int pos,
+DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, int k, int pos,
                                       int cnt) {
   bool new_max = false, do_iterate = false;
   int sel[7], samidx[7];
@@ -385,7 +385,7 @@ DG_ENG inline void replay_iteration_F(const Ctx& c, const FParams& P, Workspace&
 // One image pair, whole RANSAC.  Outputs: F (row-major, zero when no model), mask, stats
 // {samples drawn, LO runs, plane inliers (Ihmax), inlier count of the returned model}.
 // ---------------------------------------------------------------------------------------------
-DG_ENG inline void ransac_F_pair(const Ctx& c, const FParams& P, Workspace& W, double* F_out, unsigned char* mask_out,
+DG_ENGN void ransac_F_pair(const Ctx& c, const FParams& P, Workspace& W, double* F_out, unsigned char* mask_out,
                                  int* stats_out) {
   FState st;
   st.maxS = make_score(); st.maxSs = make_score();

@@ -25,14 +25,14 @@ struct HParams {
   int chunk;
 };
 
-DG_ENG inline void blk_resid_H(const Ctx& c, int metric, const double* h, double* out) {
+DG_ENGN void blk_resid_H(const Ctx& c, int metric, const double* h, double* out) {
   HSym s;
   if (metric != H_SAMPSON) h_sym_prepare(h, &s);
   for (int i = c.tid; i < c.N; i += c.nt) out[i] = h_resid_metric(metric, h, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
   DG_SYNC();
 }
 // symmetric-transfer consistency count over a list (gate: always HDsSymMaxidx, exp_ranH.c:588-597)
-DG_ENG inline unsigned blk_sym_count_H(const Ctx& c, const double* h, const int* list, int n, double sym_th) {
+DG_ENGN unsigned blk_sym_count_H(const Ctx& c, const double* h, const int* list, int n, double sym_th) {
   HSym s;
   h_sym_prepare(h, &s);
   int cnt = 0;
@@ -44,7 +44,7 @@ DG_ENG inline unsigned blk_sym_count_H(const Ctx& c, const double* h, const int*
 }
 
 // hash de-duplication shared with the F engine's table layout
-DG_ENG inline bool hash_seen_elsewhere_h(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
+DG_ENGN bool hash_seen_elsewhere_h(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
   DG_SYNC();
   if (c.tid == 0) {
     const uint32_t h = superfasthash_i32(list, n);
@@ -65,13 +65,16 @@ DG_ENG inline bool hash_seen_elsewhere_h(const Ctx& c, Workspace& W, HashTab& ht
 
 // Iterated LSQ with shrinking threshold (reference exp_iterHcustom, exp_ranH.c:291-411; inlLimit = 1e6
 // so every fit uses the whole support).
-DG_ENG inline Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, int* inl, double th, double ths,
+DG_ENGN Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, int* inl, double th, double ths,
                               double* Hio, int iterID, HashTab& ht) {
   int d = e[1];
   double h[9];
   const double dth = (ths - th) / kIlsqIters;
   Score maxS, S = make_score(), Ss;
   maxS = blk_inlidxs(c, W.err[e[4]], th, inl);
+#ifdef DG_TRACE
+  fprintf(stderr, "iterH start id=%d maxS.I=%u J=%.17g\n", iterID, maxS.I, maxS.J);
+#endif
   if (maxS.I < 4) return S;
   S = blk_inlidxs(c, W.err[e[4]], th * kMWM, inl);
   for (int i = 0; i < 9; ++i) h[i] = Hio[i];
@@ -79,6 +82,9 @@ DG_ENG inline Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int*
   for (int it = 0; it < kIlsqIters; ++it) {
     blk_resid_H(c, P.metric, h, W.err[d]);
     Ss = blk_inlidxs(c, W.err[d], th, inl);
+#ifdef DG_TRACE
+    fprintf(stderr, "iterH id=%d it=%d Ss.I=%u Ss.J=%.17g ths=%.17g\n", iterID, it, Ss.I, Ss.J, ths);
+#endif
     if (hash_seen_elsewhere_h(c, W, ht, inl, (int)Ss.I, iterID)) return make_score();
     S = blk_inlidxs(c, W.err[d], ths * kMWM, inl);
     if (score_less(maxS, Ss)) {
@@ -104,7 +110,7 @@ DG_ENG inline Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int*
 }
 
 // Inner RANSAC of the LO step (reference exp_inHranicustom, exp_ranH.c:415-467).
-DG_ENG inline Score lo_inner_H(const Ctx& c, const HParams& P, Workspace& W, int* e, int* inliers, int ninl, double th,
+DG_ENGN Score lo_inner_H(const Ctx& c, const HParams& P, Workspace& W, int* e, int* inliers, int ninl, double th,
                                double* Hout, int& iterID, DrawCursor& cur, HashTab& ht) {
   Score S, maxS = make_score();
   if (ninl < 8) return maxS;
@@ -140,7 +146,7 @@ struct HState {
 };
 
 // LO step of iter_type 4 with acceptance (exp_ranH.c:678-747 / :793-861). h: working model in/out.
-DG_ENG inline bool run_lo_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, double* h) {
+DG_ENGN bool run_lo_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, double* h) {
   bool new_max = false;
   ++st.iter_cnt;
   const int d = st.e[0];
@@ -169,7 +175,7 @@ DG_ENG inline bool run_lo_H(const Ctx& c, const HParams& P, Workspace& W, HState
 
 // WAVE over iterations kbeg..kend; survivors (J > T, or all valid models when passall) are left in
 // W.pass in iteration order (one model per iteration, so sorting by k suffices).
-DG_ENG inline int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int kend, double T, bool passall) {
+DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int kend, double T, bool passall) {
   DG_SYNC();
   if (c.tid == 0) { c.sc->counter[0] = 0; c.sc->counter[1] = 0; }
   DG_SYNC();
@@ -238,7 +244,7 @@ DG_ENG inline int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg,
 }
 
 // REPLAY of one surviving iteration (exp_ranH.c:580-756).
-DG_ENG inline void replay_iteration_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, int k, const Cand& cd) {
+DG_ENGN void replay_iteration_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, int k, const Cand& cd) {
   double h[9];
   for (int j = 0; j < 9; ++j) h[j] = cd.f[j];
   st.cur.seed = P.seed; st.cur.k = (uint32_t)k; st.cur.j = 5;
@@ -276,7 +282,7 @@ DG_ENG inline void replay_iteration_H(const Ctx& c, const HParams& P, Workspace&
 
 // One image pair.  H_out is the RAW core output: column-major, maps image 2 -> image 1 (the Python
 // layer applies inv(H.T), utils.py:108).  stats {samples, LO runs, (unused), inliers of best}.
-DG_ENG inline void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double* H_out, unsigned char* mask_out,
+DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double* H_out, unsigned char* mask_out,
                                  int* stats_out) {
   HState st;
   st.maxS = make_score(); st.maxSs = make_score();

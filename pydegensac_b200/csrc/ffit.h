@@ -44,11 +44,11 @@ struct FParams {
 };
 
 // ------------------------------------------------------------------ block-wide passes over the pair
-DG_ENG inline void blk_resid_F(const Ctx& c, int metric, const double* F, double* out) {
+DG_ENGN void blk_resid_F(const Ctx& c, int metric, const double* F, double* out) {
   for (int i = c.tid; i < c.N; i += c.nt) out[i] = f_resid(metric, F, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
   DG_SYNC();
 }
-DG_ENG inline void blk_resid_w_F(const Ctx& c, int metric, const double* F, double* out, double* w) {
+DG_ENGN void blk_resid_w_F(const Ctx& c, int metric, const double* F, double* out, double* w) {
   for (int i = c.tid; i < c.N; i += c.nt) {
     double e, ww;
     f_resid_w(metric, F, c.x1[i], c.y1[i], c.x2[i], c.y2[i], &e, &ww);
@@ -58,7 +58,7 @@ DG_ENG inline void blk_resid_w_F(const Ctx& c, int metric, const double* F, doub
   DG_SYNC();
 }
 // symmetric-epipolar consistency count over an index list (gate at exp_ranF.c:1383-1392)
-DG_ENG inline unsigned blk_sym_count_F(const Ctx& c, const double* F, const int* list, int n, double sym_th) {
+DG_ENGN unsigned blk_sym_count_F(const Ctx& c, const double* F, const int* list, int n, double sym_th) {
   int cnt = 0;
   for (int j = c.tid; j < n; j += c.nt) {
     const int i = list[j];
@@ -69,7 +69,7 @@ DG_ENG inline unsigned blk_sym_count_F(const Ctx& c, const double* F, const int*
 
 // Partial Fisher-Yates permutation of list[0..max_sz) drawing `siz` slots; the subset is the last
 // `siz` entries (reference randsubset, rtools.c:25-39).  Sequential by nature: thread 0.
-DG_ENG inline void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCursor& cur) {
+DG_ENGN void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCursor& cur) {
   DG_SYNC();
   if (c.tid == 0) {
     DrawCursor t = cur;
@@ -94,7 +94,7 @@ DG_ENG inline void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, 
 //             Ftools.c:431), i.e. a diagonal pattern; reproduced as is.
 // Result is returned to every thread in f[9].
 // ---------------------------------------------------------------------------------------------
-DG_ENG inline void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, double* f) {
+DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, double* f) {
   if (len <= 8) {
     DG_SYNC();
     if (c.tid == 0) {

@@ -19,7 +19,7 @@ DG_HD void f_lin_row(double x1, double y1, double x2, double y2, double* row) {
 // Cubic in r of det(C + r*B) with C = A - B:  p[0] r^3 + p[1] r^2 + p[2] r + p[3].
 // Same polynomial as the reference's slcm (Ftools.c:39-81), computed through cofactors; like the
 // reference it REPLACES B by A - B so that the caller mixes f = A*r + B*(1-r)  (exp_ranF.c:1366-1368).
-DG_HD void seven_pt_cubic(const double* A, double* B, double* p) {
+DG_HDN void seven_pt_cubic(const double* A, double* B, double* p) {
   double C[9];
   for (int i = 0; i < 9; ++i) C[i] = A[i] - B[i];
   double cb[9], cc[9];
@@ -40,7 +40,7 @@ DG_HD void seven_pt_cubic(const double* A, double* B, double* p) {
 
 // Real roots of po[0] x^3 + po[1] x^2 + po[2] x + po[3] (Cardano / trigonometric), the branch
 // structure of the reference's rroots3 (Ftools.c:251-298): returns 1 or 3.
-DG_HD int cubic_real_roots(const double* po, double* r) {
+DG_HDN int cubic_real_roots(const double* po, double* r) {
   const double third_pi = 1.0471975511965967;
   const double b = po[1] / po[0];
   const double c = po[2] / po[0];

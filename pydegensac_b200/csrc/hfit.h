@@ -8,11 +8,10 @@
 namespace dg {
 
 // Homography from a list of correspondences (reference u2h, Htools.c:101-133):
-//   len < 4  : nothing (h untouched);  len == 4 : exact null space (the reference's own len==4 branch
-//   transposes an 8-stride buffer as 9x9 and reads uninitialised stack, i.e. is undefined; the intended
-//   4-point solve is used here);  len > 4 : Hartley-normalised DLT, normal matrix by block reduction,
+//   len < 4  : nothing (h untouched);  len == 4 : the reference's scrambled-transpose branch (see
+//   h_from_4pt_u2h_quirk);  len > 4 : Hartley-normalised DLT, normal matrix by block reduction,
 //   smallest eigenvector (Jacobi instead of LAPACK dsyev_), de-normalisation.
-DG_ENG inline void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
+DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
   if (len < 4) return;
   if (len == 4) {
     DG_SYNC();
@@ -22,7 +21,7 @@ DG_ENG inline void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
         const int p = idx[i];
         px1[i] = c.x1[p]; py1[i] = c.y1[p]; px2[i] = c.x2[p]; py2[i] = c.y2[p];
       }
-      h_from_4pt(px1, py1, px2, py2, hh);
+      h_from_4pt_u2h_quirk(px1, py1, px2, py2, hh);
       for (int i = 0; i < 9; ++i) c.sc->bc[i] = hh[i];
     }
     bc_fetch(c, h, 9);
@@ -88,7 +87,7 @@ DG_ENG inline void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
 }
 
 // Sampson residual row of all correspondences under h (reference HDs over lin_hg, as dHDs does).
-DG_ENG inline void blk_resid_H_sampson(const Ctx& c, const double* h, double* out) {
+DG_ENGN void blk_resid_H_sampson(const Ctx& c, const double* h, double* out) {
   for (int i = c.tid; i < c.N; i += c.nt) out[i] = h_resid_sampson(h, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
   DG_SYNC();
 }

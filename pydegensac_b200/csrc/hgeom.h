@@ -69,7 +69,7 @@ DG_HD double h_resid_sampson(const double* H, double x1, double y1, double x2, d
 // Forward/backward transfer matrices for the symmetric metrics (Htools.c:202-222 and siblings):
 // Hi = h transposed into row-major (maps image2 -> image1), H1 = inverse(Hi) (maps image1 -> image2).
 struct HSym { double Hi[9]; double H1[9]; };
-DG_HD void h_sym_prepare(const double* H, HSym* s) {
+DG_HDN void h_sym_prepare(const double* H, HSym* s) {
   s->Hi[0] = H[0]; s->Hi[1] = H[3]; s->Hi[2] = H[6];
   s->Hi[3] = H[1]; s->Hi[4] = H[4]; s->Hi[5] = H[7];
   s->Hi[6] = H[2]; s->Hi[7] = H[5]; s->Hi[8] = H[8];
@@ -158,13 +158,33 @@ DG_HD void denorm_H(double* F, const double* A1, const double* A2) {
 
 // Exact 4-point homography (null space of the 8x9 DLT system; exp_ranH.c:551-566).
 // Points are given in DRAW order.  Returns false unless the null space is one-dimensional.
-DG_HD bool h_from_4pt(const double* px1, const double* py1, const double* px2, const double* py2, double* h) {
+DG_HDN bool h_from_4pt(const double* px1, const double* py1, const double* px2, const double* py2, double* h) {
   double M[81], sol[81];
   for (int i = 0; i < 4; ++i) h_lin_rows(px1[i], py1[i], px2[i], py2[i], M + 18 * i, M + 18 * i + 9);
   for (int i = 72; i < 81; ++i) M[i] = 0.0;
   const int ns = nullspace9(M, sol);
   for (int i = 0; i < 9; ++i) h[i] = sol[i];
   return ns == 1;
+}
+
+// What the reference's u2h does for len == 4 (Htools.c:108-116): lin_hg writes the 8x9 system with a
+// column stride of 8, the buffer is then transposed as if it were 9x9 (stride 9) and the last row is
+// zeroed, so the "null space" is taken of a scrambled matrix (9 of its entries come from uninitialised
+// stack, taken as 0 here).  The outcome is a model without support, i.e. that LO repetition is a no-op;
+// reproducing it keeps the LO trajectory identical to the reference's.
+DG_HDN void h_from_4pt_u2h_quirk(const double* px1, const double* py1, const double* px2, const double* py2, double* h) {
+  double Z[81], T[81], sol[81];
+  for (int i = 0; i < 81; ++i) { Z[i] = 0.0; sol[i] = 0.0; }
+  for (int i = 0; i < 4; ++i) {
+    double r0[9], r1[9];
+    h_lin_rows(px1[i], py1[i], px2[i], py2[i], r0, r1);
+    for (int c = 0; c < 9; ++c) { Z[8 * c + 2 * i] = r0[c]; Z[8 * c + 2 * i + 1] = r1[c]; }
+  }
+  for (int r = 0; r < 9; ++r)
+    for (int c = 0; c < 9; ++c) T[9 * r + c] = Z[9 * c + r];
+  for (int i = 72; i < 81; ++i) T[i] = 0.0;
+  nullspace9(T, sol);
+  for (int i = 0; i < 9; ++i) h[i] = sol[i];
 }
 
 }  // namespace dg

@@ -12,7 +12,7 @@ namespace dg {
 // column, the k-th null vector is (-column of the reduced matrix ; unit on the free column).
 // Returns the number of null vectors (written to ns[k*9 + ...]).
 // ---------------------------------------------------------------------------------------------
-DG_HD int nullspace9(double* M, double* ns) {
+DG_HDN int nullspace9(double* M, double* ns) {
   const double tol = 1e-12;
   int freec[9], pivc[9];
   int nfree = 0, npiv = 0, row = 0;
@@ -58,7 +58,7 @@ DG_HD int nullspace9(double* M, double* ns) {
 // reference reaches through lapwrap.c:67 from u2f/u2fw/u2h).  A is destroyed; on return column k of
 // V (V[r*9+k]) is the eigenvector of d[k].  Eigenvalues are NOT sorted; callers pick the minimum.
 // ---------------------------------------------------------------------------------------------
-DG_HD void jacobi_eig9(double* A, double* V, double* d) {
+DG_HDN void jacobi_eig9(double* A, double* V, double* d) {
   for (int i = 0; i < 81; ++i) V[i] = 0.0;
   for (int i = 0; i < 9; ++i) V[i * 10] = 1.0;
   for (int sweep = 0; sweep < 40; ++sweep) {
@@ -98,7 +98,7 @@ DG_HD void jacobi_eig9(double* A, double* V, double* d) {
 }
 
 // Eigenvector of the smallest eigenvalue of the symmetric 9x9 matrix C (destroyed) -> v[9].
-DG_HD void min_eigvec9(double* C, double* v) {
+DG_HDN void min_eigvec9(double* C, double* v) {
   double V[81], d[9];
   jacobi_eig9(C, V, d);
   int j = 0;
@@ -112,7 +112,7 @@ DG_HD void min_eigvec9(double* C, double* v) {
 // norms are the singular values.  Used for the rank-2 projection of F (reference singulF,
 // Ftools.c:330-347, LAPACK dgesvd_) and for the epipole in Hdetect (DegUtils.c:109, CCMATH svduv).
 // ---------------------------------------------------------------------------------------------
-DG_HD void svd3_onesided(const double* A, double* G, double* V, double* sv) {
+DG_HDN void svd3_onesided(const double* A, double* G, double* V, double* sv) {
   for (int i = 0; i < 9; ++i) { G[i] = A[i]; V[i] = 0.0; }
   V[0] = V[4] = V[8] = 1.0;
   for (int sweep = 0; sweep < 60; ++sweep) {
@@ -146,7 +146,7 @@ DG_HD void svd3_onesided(const double* A, double* G, double* V, double* sv) {
 }
 
 // Rank-2 projection F <- U diag(s0,s1,0) V^T == F - (F v_min) v_min^T   (reference: singulF)
-DG_HD void enforce_rank2(double* F) {
+DG_HDN void enforce_rank2(double* F) {
   double G[9], V[9], sv[3];
   svd3_onesided(F, G, V, sv);
   int m = 0;
@@ -157,7 +157,7 @@ DG_HD void enforce_rank2(double* F) {
 }
 
 // Right singular vector of the smallest singular value of a 3x3 row-major matrix (A v ~ 0).
-DG_HD void right_null3(const double* A, double* v) {
+DG_HDN void right_null3(const double* A, double* v) {
   double G[9], V[9], sv[3];
   svd3_onesided(A, G, V, sv);
   int m = 0;
@@ -167,11 +167,154 @@ DG_HD void right_null3(const double* A, double* v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Third right singular vector of a 3x3 row-major matrix AS CCMATH's svduv RETURNS IT
+// (matutls/svduv.c + ldvmat.c + qrbdv.c): Householder bidiagonalisation followed by Golub-Kahan-Reinsch
+// implicit-shift QR sweeps, singular values left UNSORTED.  The reference's Hdetect takes column 2 of V
+// as the epipole (DegUtils.c:109-110) whether or not the vanishing singular value ended up in slot 2
+// (it lands in slot 1 for roughly a quarter of rank-2 inputs), so the DEGENSAC test only reproduces if
+// the same sweep order is followed.  Left rotations are not accumulated (U is never used).
+// ---------------------------------------------------------------------------------------------
+DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
+  double a[9], d[3], e[2], V[9];
+  for (int i = 0; i < 9; ++i) a[i] = Ain[i];
+  e[0] = e[1] = 0.0;
+  // --- column 0 reflector
+  {
+    double w0 = a[0], w1 = a[3], w2 = a[6];
+    double s = w0 * w0 + w1 * w1 + w2 * w2, h = 0.0;
+    if (s > 0.) {
+      h = sqrt(s);
+      if (a[0] < 0.) h = -h;
+      s += a[0] * h;
+      s = 1. / s;
+      w0 += h;
+      for (int k = 1; k < 3; ++k) {
+        double r = w0 * a[k] + w1 * a[3 + k] + w2 * a[6 + k];
+        r *= s;
+        a[k] -= r * w0; a[3 + k] -= r * w1; a[6 + k] -= r * w2;
+      }
+    }
+    d[0] = -h;
+  }
+  // --- row 0 reflector over columns 1,2 (the only one that shapes V for n = 3)
+  double hb = 0.0, u2 = 0.0;  // V = I - hb * (1,u2)(1,u2)^T on the trailing 2x2 block
+  {
+    double s = a[1] * a[1] + a[2] * a[2], h = 0.0;
+    if (s > 0.) {
+      h = sqrt(s);
+      if (a[1] < 0.) h = -h;
+      hb = 1. + fabs(a[1] / h);
+      s += a[1] * h;
+      s = 1. / s;
+      const double p0 = a[1] + h;
+      const double t = 1. / p0;
+      for (int row = 1; row < 3; ++row) {
+        double r = p0 * a[3 * row + 1] + a[2] * a[3 * row + 2];
+        r *= s;
+        a[3 * row + 1] -= r * p0;
+        a[3 * row + 2] -= r * a[2];
+      }
+      u2 = a[2] * t;
+    }
+    e[0] = -h;
+  }
+  // --- column 1 reflector (rows 1,2)
+  {
+    double w0 = a[4], w1 = a[7];
+    double s = w0 * w0 + w1 * w1, h = 0.0;
+    if (s > 0.) {
+      h = sqrt(s);
+      if (a[4] < 0.) h = -h;
+      s += a[4] * h;
+      s = 1. / s;
+      w0 += h;
+      double r = w0 * a[5] + w1 * a[8];
+      r *= s;
+      a[5] -= r * w0; a[8] -= r * w1;
+    }
+    d[1] = -h;
+  }
+  e[1] = a[5];
+  d[2] = a[8];
+  for (int i = 0; i < 9; ++i) V[i] = 0.0;
+  V[0] = 1.0; V[4] = 1.0; V[8] = 1.0;
+  if (hb != 0.) {
+    V[4] = 1. - hb;
+    V[7] = -hb * u2;
+    const double sdot = hb * u2;      // (V[8]=1) * u2 * hb
+    V[8] = 1. - sdot * u2;
+    V[5] = -sdot;
+  }
+  // --- implicit-shift QR sweeps on the bidiagonal (d,e)
+  int m = 3;
+  double t = fabs(d[0]);
+  for (int j = 1; j < 3; ++j) {
+    const double s = fabs(d[j]) + fabs(e[j - 1]);
+    if (s > t) t = s;
+  }
+  t *= 1.e-15;
+  for (int it = 0; m > 1 && it < 300; ++it) {
+    int k;
+    for (k = m - 1; k > 0; --k) {
+      if (fabs(e[k - 1]) < t) break;
+      if (fabs(d[k - 1]) < t) {
+        double s = 1., c = 0.;
+        for (int i = k; i < m; ++i) {
+          const double aa = s * e[i - 1], bb = d[i];
+          e[i - 1] *= c;
+          const double u = sqrt(aa * aa + bb * bb);
+          d[i] = u;
+          s = -aa / u;
+          c = bb / u;
+        }
+        break;
+      }
+    }
+    double y = d[k], x = d[m - 1], u = e[m - 2];
+    double aa = (y + x) * (y - x) - u * u, s = y * e[k], bb = s + s;
+    u = sqrt(aa * aa + bb * bb);
+    if (u != 0.) {
+      double c = sqrt((u + aa) / (u + u));
+      if (c != 0.) s /= (c * u); else s = 1.;
+      for (int i = k; i < m - 1; ++i) {
+        bb = e[i];
+        if (i > k) {
+          aa = s * e[i];
+          bb *= c;
+          e[i - 1] = u = sqrt(x * x + aa * aa);
+          c = x / u;
+          s = aa / u;
+        }
+        aa = c * y + s * bb;
+        bb = c * bb - s * y;
+        for (int r = 0; r < 3; ++r) {
+          const double w = c * V[3 * r + i] + s * V[3 * r + i + 1];
+          V[3 * r + i + 1] = c * V[3 * r + i + 1] - s * V[3 * r + i];
+          V[3 * r + i] = w;
+        }
+        s *= d[i + 1];
+        d[i] = u = sqrt(aa * aa + s * s);
+        y = c * d[i + 1];
+        c = aa / u;
+        s /= u;
+        x = c * bb + s * y;
+        y = c * y - s * bb;
+      }
+    }
+    e[m - 2] = x;
+    d[m - 1] = y;
+    if (fabs(x) < t) --m;
+    if (m == k + 1) --m;
+  }
+  vout[0] = V[2]; vout[1] = V[5]; vout[2] = V[8];  // the sign flip svduv applies for d[2] < 0 does not matter
+}
+
+// ---------------------------------------------------------------------------------------------
 // Unit vector orthogonal to the `len` (<= 8) columns of the 9 x len row-major matrix Z (destroyed):
 // the last column of the full Q of a Householder QR.  This is what the reference takes from CCMATH
 // svduv as "last column of U" in the len <= 8 branch of u2f/u2fw (Ftools.c:373,383,433,443).
 // ---------------------------------------------------------------------------------------------
-DG_HD void left_null_9xk(double* Z, int len, double* q) {
+DG_HDN void left_null_9xk(double* Z, int len, double* q) {
   double vs[8][9];
   double beta[8];
   for (int c = 0; c < len; ++c) {
@@ -207,7 +350,7 @@ DG_HD void left_null_9xk(double* Z, int len, double* q) {
 // 3x3 inverse in place (row-major) by Gauss-Jordan with partial pivoting.  Returns nonzero when a
 // pivot falls below 1e-15 x the largest pivot seen so far (the singularity rule of CCMATH minv,
 // matutls/minv.c:11,27), in which case the matrix content is unspecified.
-DG_HD int inv3(double* a) {
+DG_HDN int inv3(double* a) {
   double m[3][6];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) { m[i][j] = a[3 * i + j]; m[i][3 + j] = (i == j) ? 1.0 : 0.0; }

@@ -1,0 +1,189 @@
+"""Python API of the reference (src/pydegensac/utils.py:15-146), same names, arguments, defaults,
+validation and return conventions, on top of the B200 engine.
+
+Additive: `seed=None` on both functions (the reference seeds libc rand() from time(NULL) inside the C
+core and cannot be made reproducible); batched entry points `findFundamentalMatrixBatch` /
+`findHomographyBatch` for [P,N,2] stacks of independent image pairs.
+"""
+import math
+import os
+import warnings
+
+import numpy as np
+
+try:
+    import cv2
+    OPENCV_HERE = True
+except Exception:  # pragma: no cover
+    OPENCV_HERE = False
+
+error_type_dict_homography = {"sampson": 0,
+                              "symm_sq_max": 1,
+                              "symm_max": 2,
+                              "symm_sq_sum": 3,
+                              "symm_sum": 4}
+
+error_type_dict_fundamental = {"sampson": 0,
+                               "symm_epipolar": 1}
+
+
+def _native():
+    """The pybind11 module (bindings.cpp surface). Import lazily so that the pure-Python validation layer can
+    be exercised without the native build; any compute call without it raises loudly."""
+    from . import _cabi
+    _cabi.lib()  # raises EngineUnavailable with build instructions if the CUDA library is missing
+    from . import pydegensac as native
+    return native
+
+
+def convert_cv2_kpts_to_xyA(kps):
+    """cv2.KeyPoint list -> [N,6] (x, y, a11, a12, a21, a22)   (reference utils.py:24-41)."""
+    num = len(kps)
+    out = np.zeros((num, 6)).astype(np.float64)
+    for i, kp in enumerate(kps):
+        out[i, :2] = kp.pt
+        s = kp.size
+        a = kp.angle
+        cos = math.cos(a * math.pi / 180.0)
+        sin = math.sin(a * math.pi / 180.0)
+        out[i, 2] = s * cos
+        out[i, 3] = s * sin
+        out[i, 4] = -s * sin
+        out[i, 5] = s * cos
+    return out
+
+
+def convert_and_check(kps1):
+    """Input validation of the reference (utils.py:43-71)."""
+    if type(kps1) is np.ndarray:
+        sh = kps1.shape
+        err_message = ValueError("Keypoints should be list of cv2.KeyPoint or numpy.array [Nx2] or [Nx6]. N>=4 "
+                                 "Got shape of {} with shape instead".format(str(sh)))
+        if len(sh) != 2:
+            raise err_message
+        num, dim = sh
+        if (dim != 2) and (dim != 6):
+            raise err_message
+        if num < 4:
+            raise err_message
+        out = kps1.astype(np.float64)
+    elif type(kps1) is list:
+        if OPENCV_HERE:
+            if type(kps1[0]) is not cv2.KeyPoint:
+                raise ValueError("Keypoints should be list of cv2.KeyPoint or numpy.array [Nx2] or [Nx6]. N>=4 "
+                                 "Got input of list of type {}".format(str(type(kps1[0]))))
+            out = convert_cv2_kpts_to_xyA(kps1)
+        else:
+            raise ValueError("Cannot import cv2. Please, install or pass np.arrays instead")
+    else:
+        raise ValueError("Keypoints should be list of cv2.KeyPoint or numpy.array [Nx2] or [Nx6]. N>=4 "
+                         "Got input of type {}".format(str(type(kps1))))
+    return out
+
+
+def _seed_value(seed):
+    if seed is None:
+        return int.from_bytes(os.urandom(8), "little")
+    return int(seed) & 0xFFFFFFFFFFFFFFFF
+
+
+def _error_type(error_type, table):
+    try:
+        return table[error_type.lower()]
+    except Exception:
+        raise ValueError("Error type should be on of {}. Got {} instead".format(list(table.keys()), error_type))
+
+
+def findHomography(pts1_,
+                   pts2_,
+                   px_th=1.0,
+                   conf=0.999,
+                   max_iters=50000,
+                   laf_consistensy_coef=-1.0,
+                   error_type="sampson",
+                   symmetric_error_check=True,
+                   seed=None):
+    """Reference utils.py:74-109. Returns (H 3x3 in OpenCV convention x2 ~ H x1, mask)."""
+    pts1 = convert_and_check(pts1_)
+    pts2 = convert_and_check(pts2_)
+    n, dim = pts1.shape
+    n2, dim2 = pts2.shape
+    assert (n == n2) and (dim == dim2)
+    if dim == 2 and laf_consistensy_coef > 0:
+        warnings.warn('You set laf_consistensy_coef, but provided only (x,y) keypoints. Skipping LAF check')
+        laf_consistensy_coef = 0
+    error_type_int = _error_type(error_type, error_type_dict_homography)
+    laf_consistensy_coef = max(0, laf_consistensy_coef)
+    H, mask = _native().findHomography_(pts1, pts2, px_th, conf, max_iters, error_type_int, symmetric_error_check,
+                                        laf_consistensy_coef, _seed_value(seed))
+    if np.abs(H).sum() == 0:
+        # If we haven`t found any good model, output zeros
+        mask = [False] * len(mask)
+        return H, mask
+    H_out = np.linalg.inv(H.T)
+    return H_out, mask
+
+
+def findFundamentalMatrix(pts1_,
+                          pts2_,
+                          px_th=0.5,
+                          conf=0.9999,
+                          max_iters=100000,
+                          laf_consistensy_coef=-1.0,
+                          error_type="sampson",
+                          symmetric_error_check=True,
+                          enable_degeneracy_check=True,
+                          seed=None):
+    """Reference utils.py:111-146. Returns (F 3x3 with x2^T F x1 = 0, mask)."""
+    pts1 = convert_and_check(pts1_)
+    pts2 = convert_and_check(pts2_)
+    n, dim = pts1.shape
+    n2, dim2 = pts2.shape
+    assert (n == n2) and (dim == dim2)
+    if dim == 2 and laf_consistensy_coef > 0:
+        warnings.warn('You set laf_consistensy_coef, but provided only (x,y) keypoints. Skipping LAF check')
+        laf_consistensy_coef = 0
+    error_type_int = _error_type(error_type, error_type_dict_fundamental)
+    laf_consistensy_coef = max(0, laf_consistensy_coef)
+    F, mask = _native().findFundamentalMatrix_(pts1, pts2, px_th, conf, max_iters, error_type_int,
+                                               symmetric_error_check, laf_consistensy_coef, enable_degeneracy_check,
+                                               _seed_value(seed))
+    if np.abs(F).sum() == 0:
+        # If we haven`t found any good model, output zeros
+        mask = [False] * n
+    return F, mask
+
+
+def _batch_seeds(seeds, P):
+    if seeds is None:
+        base = _seed_value(None)
+        return (np.arange(P, dtype=np.uint64) + np.uint64(base & 0x7FFFFFFFFFFFFFFF))
+    return seeds
+
+
+def findFundamentalMatrixBatch(pts1, pts2, px_th=0.5, conf=0.9999, max_iters=100000, error_type="sampson",
+                               symmetric_error_check=True, enable_degeneracy_check=True, seeds=None,
+                               return_stats=False):
+    """Batched findFundamentalMatrix over P independent pairs: pts [P,N,2] -> (F [P,3,3], mask [P,N] bool).
+    Pairs without a model get an all-zero F and an all-False mask row."""
+    from . import _cabi
+    et = _error_type(error_type, error_type_dict_fundamental)
+    p1 = np.asarray(pts1)
+    F, mask, stats = _cabi.fundamental_batch(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check, 0.0,
+                                             enable_degeneracy_check, _batch_seeds(seeds, p1.shape[0]))
+    return (F, mask, stats) if return_stats else (F, mask)
+
+
+def findHomographyBatch(pts1, pts2, px_th=1.0, conf=0.999, max_iters=50000, error_type="sampson",
+                        symmetric_error_check=True, seeds=None, return_stats=False):
+    """Batched findHomography: pts [P,N,2] -> (H [P,3,3] OpenCV convention, mask [P,N] bool)."""
+    from . import _cabi
+    et = _error_type(error_type, error_type_dict_homography)
+    p1 = np.asarray(pts1)
+    Hraw, mask, stats = _cabi.homography_batch(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check, 0.0,
+                                               _batch_seeds(seeds, p1.shape[0]))
+    H = np.zeros_like(Hraw)
+    for i in range(Hraw.shape[0]):
+        if np.abs(Hraw[i]).sum() != 0:
+            H[i] = np.linalg.inv(Hraw[i].T)
+    return (H, mask, stats) if return_stats else (H, mask)

@@ -85,3 +85,4 @@ extern "C" int emu_checksample(const double* F, const double* u7, double th, dou
   for (int t = 0; t < 5; ++t) if (checksample_triplet(F, u7, t, th, H)) return 1;
   return 0;
 }
+extern "C" void emu_gkr_v3(const double* A, double* v) { gkr_third_right_vector3(A, v); }
