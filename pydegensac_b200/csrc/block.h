@@ -6,6 +6,7 @@
 #pragma once
 #include "common.h"
 #include "la.h"
+#include "warpla.h"
 
 namespace dg {
 
@@ -20,6 +21,7 @@ struct BlockScratch {
   double bc[32];                   // broadcast area for small results (models, scalars)
   int bci[16];
   int counter[4];                  // atomic counters of the hypothesis wave
+  WarpScratch ws[5];               // per-warp tiles for the cooperative 9x9 solves (5 = checksample triplets)
 };
 
 struct Ctx {

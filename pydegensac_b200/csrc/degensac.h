@@ -66,68 +66,91 @@ DG_HDN void h_from_F_3pts(const double* F, const double* u7, const int* tri, dou
   }
 }
 
-// One-thread normalised DLT on a handful of points given explicitly (the 5-point refit of checksample).
-DG_HDN void h_fit_small(const double* u7, const int* idx, int len, double* h) {
+// Normalised DLT on a handful of points of the sample (the 5-point refit of checksample), warp-cooperative:
+// lane 0 normalises and writes the 2*len DLT rows, the lanes form the normal matrix and run the Jacobi sweeps.
+// Result (lane 0): h[9].
+DG_ENGN void warp_h_fit_small(WarpScratch* ws, const double* u7, const int* idx, int len, double* h, int lane, int W) {
   double A1[3] = {0, 0, 0}, A2[3] = {0, 0, 0};
-  for (int j = 0; j < len; ++j) {
-    const double* p = u7 + 4 * idx[j];
-    A1[1] += p[0]; A1[2] += p[1]; A2[1] += p[2]; A2[2] += p[3];
-  }
-  for (int i = 1; i < 3; ++i) { A1[i] /= len; A2[i] /= len; }
-  for (int j = 0; j < len; ++j) {
-    const double* p = u7 + 4 * idx[j];
-    double a = p[0] - A1[1], b = p[1] - A1[2];
-    A1[0] += sqrt(a * a + b * b);
-    a = p[2] - A2[1]; b = p[3] - A2[2];
-    A2[0] += sqrt(a * a + b * b);
-  }
-  if (A1[0] != 0) A1[0] = len * sqrt(2.0) / A1[0];
-  if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
-  A1[1] *= -A1[0]; A1[2] *= -A1[0];
-  A2[1] *= -A2[0]; A2[2] *= -A2[0];
-  double C[81];
-  for (int i = 0; i < 81; ++i) C[i] = 0.0;
-  for (int j = 0; j < len; ++j) {
-    const double* p = u7 + 4 * idx[j];
-    double a[3], b[3], r0[9], r1[9];
-    a[0] = p[0] * A1[0] + A1[1]; a[1] = p[1] * A1[0] + A1[2]; a[2] = 1.0;
-    b[0] = p[2] * A2[0] + A2[1]; b[1] = p[3] * A2[0] + A2[2]; b[2] = 1.0;
-    for (int t = 0; t < 3; ++t) {
-      r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
-      r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
+  double* rows = ws->aux;   // 2*len x 9, len <= 6
+  if (lane == 0) {
+    for (int j = 0; j < len; ++j) {
+      const double* p = u7 + 4 * idx[j];
+      A1[1] += p[0]; A1[2] += p[1]; A2[1] += p[2]; A2[2] += p[3];
     }
-    for (int i = 0; i < 9; ++i)
-      for (int jj = 0; jj <= i; ++jj) {
-        C[9 * i + jj] += r0[i] * r0[jj];
-        C[9 * i + jj] += r1[i] * r1[jj];
+    for (int i = 1; i < 3; ++i) { A1[i] /= len; A2[i] /= len; }
+    for (int j = 0; j < len; ++j) {
+      const double* p = u7 + 4 * idx[j];
+      double a = p[0] - A1[1], b = p[1] - A1[2];
+      A1[0] += sqrt(a * a + b * b);
+      a = p[2] - A2[1]; b = p[3] - A2[2];
+      A2[0] += sqrt(a * a + b * b);
+    }
+    if (A1[0] != 0) A1[0] = len * sqrt(2.0) / A1[0];
+    if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
+    A1[1] *= -A1[0]; A1[2] *= -A1[0];
+    A2[1] *= -A2[0]; A2[2] *= -A2[0];
+    for (int j = 0; j < len; ++j) {
+      const double* p = u7 + 4 * idx[j];
+      double a[3], b[3];
+      a[0] = p[0] * A1[0] + A1[1]; a[1] = p[1] * A1[0] + A1[2]; a[2] = 1.0;
+      b[0] = p[2] * A2[0] + A2[1]; b[1] = p[3] * A2[0] + A2[2]; b[2] = 1.0;
+      double* r0 = rows + 18 * j;
+      double* r1 = r0 + 9;
+      for (int t = 0; t < 3; ++t) {
+        r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
+        r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
       }
+    }
   }
-  for (int i = 0; i < 9; ++i)
-    for (int jj = 0; jj < i; ++jj) C[9 * jj + i] = C[9 * i + jj];
-  min_eigvec9(C, h);
-  denorm_H(h, A1, A2);
+  DG_WSYNC();
+  for (int t = lane; t < 45; t += W) {
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    const int jj = t - i * (i + 1) / 2;
+    double s = 0.0;
+    for (int r = 0; r < 2 * len; ++r) s += rows[9 * r + i] * rows[9 * r + jj];
+    ws->A[9 * i + jj] = s;
+    ws->A[9 * jj + i] = s;
+  }
+  DG_WSYNC();
+  warp_jacobi_eig9(ws, lane, W);
+  DG_WSYNC();
+  if (lane == 0) {
+    int m = 0;
+    for (int i = 1; i < 9; ++i)
+      if (ws->A[i * 10] < ws->A[m * 10]) m = i;
+    for (int i = 0; i < 9; ++i) h[i] = ws->V[i * 9 + m];
+    denorm_H(h, A1, A2);
+  }
+  DG_WSYNC();
 }
 
-// One triplet of the degeneracy test (body of the loop in checksample, DegUtils.c:55-80).
-DG_HDN bool checksample_triplet(const double* F, const double* u7, int t, double th, double* H) {
+// One triplet of the degeneracy test (body of the loop in checksample, DegUtils.c:55-80), one warp.
+// Verdict and H are valid on lane 0.
+DG_ENGN bool warp_checksample_triplet(WarpScratch* ws, const double* F, const double* u7, int t, double th, double* H,
+                                      int lane, int W) {
   const int TRI[5][3] = {{0, 1, 2}, {3, 4, 5}, {0, 1, 6}, {3, 4, 6}, {2, 5, 6}};
-  h_from_F_3pts(F, u7, TRI[t], H);
-  double Ds[7];
-  int idx[7];
-  for (int j = 0; j < 7; ++j) {
-    Ds[j] = h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]);
-    idx[j] = j;
+  int* idx = reinterpret_cast<int*>(ws->cs + 8);   // 7 ints shared with the other lanes
+  if (lane == 0) {
+    h_from_F_3pts(F, u7, TRI[t], H);
+    double Ds[7];
+    for (int j = 0; j < 7; ++j) {
+      Ds[j] = h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]);
+      idx[j] = j;
+    }
+    for (int i = 0; i < 7; ++i)      // exchange sort of the reference's sortDs (DegUtils.c:164-183)
+      for (int j = i + 1; j < 7; ++j)
+        if (Ds[j] < Ds[i]) {
+          const double td = Ds[j]; Ds[j] = Ds[i]; Ds[i] = td;
+          const int ti = idx[j]; idx[j] = idx[i]; idx[i] = ti;
+        }
   }
-  for (int i = 0; i < 7; ++i)      // exchange sort of the reference's sortDs (DegUtils.c:164-183)
-    for (int j = i + 1; j < 7; ++j)
-      if (Ds[j] < Ds[i]) {
-        const double td = Ds[j]; Ds[j] = Ds[i]; Ds[i] = td;
-        const int ti = idx[j]; idx[j] = idx[i]; idx[i] = ti;
-      }
-  h_fit_small(u7, idx, 5, H);
+  DG_WSYNC();
+  warp_h_fit_small(ws, u7, idx, 5, H, lane, W);
   int cnt = 0;
-  for (int j = 0; j < 7; ++j)
-    if (h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]) < th) ++cnt;
+  if (lane == 0)
+    for (int j = 0; j < 7; ++j)
+      if (h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]) < th) ++cnt;
   return cnt > 4;
 }
 
@@ -136,13 +159,16 @@ DG_HDN bool checksample_triplet(const double* F, const double* u7, int t, double
 DG_ENGN bool blk_checksample(const Ctx& c, const double* F, const double* u7, double th, double* H) {
   DG_SYNC();
   const int par = (c.nw >= 5) ? 5 : 1;
-  if (c.lane == 0 && c.wid < par) {
+  const int W = DG_DEVICE_PASS ? 32 : 1;
+  if (c.wid < par) {
     for (int t = c.wid; t < 5; t += par) {
       double Ht[9];
-      const bool ok = checksample_triplet(F, u7, t, th, Ht);
-      c.sc->bci[t] = ok ? 1 : 0;
-      if (t < 3) { for (int i = 0; i < 9; ++i) c.sc->bc[9 * t + i] = Ht[i]; }
-      else { for (int i = 0; i < 9; ++i) c.sc->vec[9 * (t - 3) + i] = Ht[i]; }
+      const bool ok = warp_checksample_triplet(&c.sc->ws[c.wid], F, u7, t, th, Ht, c.lane, W);
+      if (c.lane == 0) {
+        c.sc->bci[t] = ok ? 1 : 0;
+        if (t < 3) { for (int i = 0; i < 9; ++i) c.sc->bc[9 * t + i] = Ht[i]; }
+        else { for (int i = 0; i < 9; ++i) c.sc->vec[9 * (t - 3) + i] = Ht[i]; }
+      }
     }
   }
   DG_SYNC();

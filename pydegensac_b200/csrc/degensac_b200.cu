@@ -19,6 +19,10 @@
 #include "engine_h.h"
 #include "workspace.h"
 
+#ifdef DG_PROF
+__device__ unsigned long long g_dg_prof[32];
+#endif
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -333,6 +337,12 @@ int dgb200_set_device(int device) {
 const char* dgb200_last_error(void) { return g_err; }
 long long dgb200_kernel_launches(void) { return g_launches; }
 double dgb200_last_kernel_ms(void) { return g_last_ms; }
+#ifdef DG_PROF
+void dgb200_prof_read(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, g_dg_prof, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_dg_prof, z, sizeof(z)); }
+}
+#endif
 void dgb200_release(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_c.device >= 0) cudaSetDevice(g_c.device);

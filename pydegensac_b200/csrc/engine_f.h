@@ -35,6 +35,7 @@ namespace dg {
 // (hash.c:49-96, exp_ranF.c:675-686).  Only "(hash,len) seen under this iterID / another iterID /
 // never" matters, so a flat list is equivalent.  Returns true when the refinement must abort.
 DG_ENGN bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
+  DG_PROF_BEGIN(4);
   DG_SYNC();
   if (c.tid == 0) {
     const uint32_t h = superfasthash_i32(list, n);
@@ -53,6 +54,7 @@ DG_ENGN bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, const 
   const int verdict = c.sc->bci[0];
   DG_SYNC();
   if (verdict == 0 && ht.n < W.hcap) ++ht.n;
+  DG_PROF_END(4);
   return verdict == 2;
 }
 
@@ -154,6 +156,7 @@ struct FState {
 DG_ENGN bool run_lo_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, const double* src_row) {
   double f[9];
   bool new_max = false;
+  DG_PROF_BEGIN(3);
   ++st.iter_cnt;
   const int d = st.e[0];
   Score S = blk_inlidxs(c, src_row, kTC * P.th * kMWM, W.inliers);
@@ -174,6 +177,7 @@ DG_ENGN bool run_lo_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, 
       new_max = true;
     }
   }
+  DG_PROF_END(3);
   return new_max;
 }
 
@@ -189,6 +193,7 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
   if (c.tid == 0) { c.sc->counter[0] = 0; c.sc->counter[1] = 0; c.sc->counter[2] = 0; }
   DG_SYNC();
   // stage A: one thread per minimal sample
+  DG_PROF_BEGIN(0);
   for (int k = kbeg + c.tid; k <= kend; k += c.nt) {
     int sel[7];
     minimal_sample<7>(P.seed, (uint32_t)k, c.N, sel);
@@ -225,6 +230,8 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
     }
   }
   DG_SYNC();
+  DG_PROF_END(0);
+  DG_PROF_BEGIN(1);
   int ncand = c.sc->counter[0];
   if (ncand > W.cand_cap) ncand = W.cand_cap;
   *valid_itersam = (c.sc->counter[2] != 0);
@@ -253,6 +260,7 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
     }
   }
   DG_SYNC();
+  DG_PROF_END(1);
   const int npass = c.sc->counter[1];
   // order survivors by (iteration, root): small list, thread 0 insertion sort
   if (c.tid == 0) {
@@ -297,6 +305,7 @@ DG_ENGN void final_mask_F(const Ctx& c, const FParams& P, Workspace& W, FState& 
 DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, int k, int pos,
                                       int cnt) {
   bool new_max = false, do_iterate = false;
+  DG_PROF_BEGIN(2);
   int sel[7], samidx[7];
   minimal_sample<7>(P.seed, (uint32_t)k, c.N, sel);
   for (int t = 0; t < 7; ++t) samidx[t] = sel[6 - t];
@@ -332,12 +341,15 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
           const int p = samidx[t];
           u7[4 * t] = c.x1[p]; u7[4 * t + 1] = c.y1[p]; u7[4 * t + 2] = c.x2[p]; u7[4 * t + 3] = c.y2[p];
         }
+        DG_PROF_BEGIN(5);
         degenerate = blk_checksample(c, f, u7, 3 * P.th, H);
+        DG_PROF_END(5);
       }
       if (degenerate) {
+        DG_PROF_BEGIN(6);
         blk_resid_H_sampson(c, H, W.dtmp[4]);
         unsigned I = (unsigned)blk_count_lt(c, W.dtmp[4], P.th * 3);
-        if (I < 8) break;
+        if (I < 8) { DG_PROF_END(6); break; }
         I = blk_inner_H(c, W, H, 16 * P.th, 10, W.btmp[0], st.cur);
         if ((int)I > st.Ihmax) st.Ihmax = (int)I;
         if (I > 6) {
@@ -360,6 +372,7 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
           if (new_max) st.maxS.J = jj;
           ++st.degen_cnt;
         }
+        DG_PROF_END(6);
       } else {
         do_iterate = (k > kIterSam);
         st.e[4] = d;
@@ -379,6 +392,7 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
       if (new_sam < st.max_sam) st.max_sam = new_sam;
     }
   }
+  DG_PROF_END(2);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -96,33 +96,41 @@ DG_ENGN void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCu
 // ---------------------------------------------------------------------------------------------
 DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, double* f) {
   if (len <= 8) {
+    DG_PROF_BEGIN(7);
     DG_SYNC();
-    if (c.tid == 0) {
-      double Z[72];
-      for (int i = 0; i < len; ++i) {
+    if (c.wid == 0) {   // warp 0: one lane per column of the 9 x len system, Householder QR across the lanes
+      WarpScratch* ws = &c.sc->ws[0];
+      const int W = DG_DEVICE_PASS ? 32 : 1;
+      for (int i = c.lane; i < len; i += W) {
         const int p = idx[i];
         double row[9];
         f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], row);
-        for (int r = 0; r < 9; ++r) Z[r * len + i] = row[r];
+        for (int r = 0; r < 9; ++r) ws->A[r * len + i] = row[r];
       }
+      DG_WSYNC();
       if (w) {
-        for (int i = 0; i < len; ++i) {
+        for (int i = c.lane; i < len; i += W) {
           const double wi = w[idx[i]];
           for (int t = 0; t < 9; ++t) {
             const int lin = i + 9 * t;
-            if (lin < 9 * len) Z[lin] *= wi;
+            if (lin < 9 * len) ws->A[lin] *= wi;
           }
         }
+        DG_WSYNC();
       }
-      double q[9];
-      if (len > 0) left_null_9xk(Z, len, q);
-      else for (int i = 0; i < 9; ++i) q[i] = (i == 8) ? 1.0 : 0.0;
-      enforce_rank2(q);
-      for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+      if (len > 0) warp_left_null_9xk(ws, len, c.lane, W);
+      if (c.lane == 0) {
+        double q[9];
+        for (int i = 0; i < 9; ++i) q[i] = (len > 0) ? ws->cs[i] : ((i == 8) ? 1.0 : 0.0);
+        enforce_rank2(q);
+        for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+      }
     }
     bc_fetch(c, f, 9);
+    DG_PROF_END(7);
     return;
   }
+  DG_PROF_BEGIN(8);
   // Hartley normalisation (reference normu, utools.c:7-51)
   double v[kVecRed];
   for (int i = 0; i < 4; ++i) v[i] = 0.0;
@@ -164,21 +172,19 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
       for (int jj = 0; jj <= i; ++jj) v[t++] += row[i] * row[jj];
   }
   blk_sum_vec(c, v, 45);
-  if (c.tid == 0) {
-    double C[81], q[9];
-    int t = 0;
-    for (int i = 0; i < 9; ++i)
-      for (int jj = 0; jj <= i; ++jj) {
-        const double s = c.sc->vec_out[t++];
-        C[9 * i + jj] = s;
-        C[9 * jj + i] = s;
-      }
-    min_eigvec9(C, q);
-    enforce_rank2(q);
-    denorm_F(q, A1, A2);
-    for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+  if (c.wid == 0) {   // warp 0: parallel-order Jacobi on the 9x9 normal matrix
+    WarpScratch* ws = &c.sc->ws[0];
+    warp_min_eigvec9_packed(ws, c.sc->vec_out, c.lane, DG_DEVICE_PASS ? 32 : 1);
+    if (c.lane == 0) {
+      double q[9];
+      for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
+      enforce_rank2(q);
+      denorm_F(q, A1, A2);
+      for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+    }
   }
   bc_fetch(c, f, 9);
+  DG_PROF_END(8);
 }
 
 }  // namespace dg

@@ -70,18 +70,15 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
       }
   }
   blk_sum_vec(c, v, 45);
-  if (c.tid == 0) {
-    double C[81], q[9];
-    int t = 0;
-    for (int i = 0; i < 9; ++i)
-      for (int jj = 0; jj <= i; ++jj) {
-        const double s = c.sc->vec_out[t++];
-        C[9 * i + jj] = s;
-        C[9 * jj + i] = s;
-      }
-    min_eigvec9(C, q);
-    denorm_H(q, A1, A2);
-    for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+  if (c.wid == 0) {
+    WarpScratch* ws = &c.sc->ws[0];
+    warp_min_eigvec9_packed(ws, c.sc->vec_out, c.lane, DG_DEVICE_PASS ? 32 : 1);
+    if (c.lane == 0) {
+      double q[9];
+      for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
+      denorm_H(q, A1, A2);
+      for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+    }
   }
   bc_fetch(c, h, 9);
 }

@@ -67,7 +67,7 @@ DG_HDN void jacobi_eig9(double* A, double* V, double* d) {
       dia += A[p * 10] * A[p * 10];
       for (int q = p + 1; q < 9; ++q) off += A[p * 9 + q] * A[p * 9 + q];
     }
-    if (!(off > 1e-34 * dia) || off == 0.0) break;
+    if (!(off > 4e-30 * dia) || off == 0.0) break;  // off-norm at rounding level: converged
     for (int p = 0; p < 8; ++p) {
       for (int q = p + 1; q < 9; ++q) {
         const double apq = A[p * 9 + q];
@@ -125,7 +125,7 @@ DG_HDN void svd3_onesided(const double* A, double* G, double* V, double* sv) {
           be += G[3 * i + q] * G[3 * i + q];
           ga += G[3 * i + p] * G[3 * i + q];
         }
-        if (ga == 0.0 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+        if (ga == 0.0 || fabs(ga) <= 1e-15 * sqrt(al * be)) continue;  // orthogonal to rounding level
         rotated = true;
         const double zeta = (be - al) / (2.0 * ga);
         const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));

@@ -82,7 +82,8 @@ extern "C" void emu_minimal_sample(uint64_t seed, uint32_t k, int N, int m, int*
 }
 extern "C" uint32_t emu_value31(uint64_t seed, uint32_t k, uint32_t j) { return value31(seed, k, j); }
 extern "C" int emu_checksample(const double* F, const double* u7, double th, double* H) {
-  for (int t = 0; t < 5; ++t) if (checksample_triplet(F, u7, t, th, H)) return 1;
+  static WarpScratch ws;
+  for (int t = 0; t < 5; ++t) if (warp_checksample_triplet(&ws, F, u7, t, th, H, 0, 1)) return 1;
   return 0;
 }
 extern "C" void emu_gkr_v3(const double* A, double* v) { gkr_third_right_vector3(A, v); }
