@@ -133,6 +133,16 @@ DG_ENGN bool warp_checksample_triplet(WarpScratch* ws, const double* F, const do
   int* idx = reinterpret_cast<int*>(ws->cs + 8);   // 7 ints shared with the other lanes
   if (lane == 0) {
     h_from_F_3pts(F, u7, TRI[t], H);
+#ifdef DG_TRACE
+    if (t == 0) {
+      fprintf(stderr, "CSIN F=");
+      for (int i = 0; i < 9; ++i) fprintf(stderr, "%.17g ", F[i]);
+      fprintf(stderr, "u7=");
+      for (int i = 0; i < 28; ++i) fprintf(stderr, "%.17g ", u7[i]);
+      fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "HDET t=%d H=%.10g %.10g %.10g %.10g\n", t, H[0], H[1], H[2], H[8]);
+#endif
     double Ds[7];
     for (int j = 0; j < 7; ++j) {
       Ds[j] = h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]);
@@ -151,6 +161,13 @@ DG_ENGN bool warp_checksample_triplet(WarpScratch* ws, const double* F, const do
   if (lane == 0)
     for (int j = 0; j < 7; ++j)
       if (h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]) < th) ++cnt;
+#ifdef DG_TRACE
+  if (lane == 0) {
+    double Ds[7];
+    for (int j = 0; j < 7; ++j) Ds[j] = h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]);
+    fprintf(stderr, "CS trip=%d cnt=%d Ds=%.6g %.6g %.6g %.6g %.6g %.6g %.6g H=%.10g %.10g %.10g\n", t, cnt, Ds[0], Ds[1], Ds[2], Ds[3], Ds[4], Ds[5], Ds[6], H[0] / H[8], H[1] / H[8], H[2] / H[8]);
+  }
+#endif
   return cnt > 4;
 }
 
@@ -242,6 +259,9 @@ DG_ENGN unsigned blk_inner_H(const Ctx& c, Workspace& W, double* H, double th, u
   blk_resid_H_sampson(c, H, rows[e[0]]);
   Score S = blk_inlidxs(c, rows[e[0]], th, inliers);
   const int ninl = (int)S.I;
+#ifdef DG_TRACE
+  fprintf(stderr, "innerH start I=%u\n", S.I);
+#endif
   if (ninl >= 8) {  // inHrani
     Score maxS = make_score();
     int ssiz = ninl / 2;

@@ -332,6 +332,9 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
       new_max = true;
     }
     if (score_less(st.maxSs, S)) {
+#ifdef DG_TRACE
+      fprintf(stderr, "BS k=%d root=%d S.I=%u S.J=%.17g maxS.J=%.17g\n", k, i, S.I, S.J, st.maxS.J);
+#endif
       st.maxSs = S;
       bool degenerate = false;
       double H[9];

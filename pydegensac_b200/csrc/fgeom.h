@@ -17,25 +17,31 @@ DG_HD void f_lin_row(double x1, double y1, double x2, double y2, double* row) {
 }
 
 // Cubic in r of det(C + r*B) with C = A - B:  p[0] r^3 + p[1] r^2 + p[2] r + p[3].
-// Same polynomial as the reference's slcm (Ftools.c:39-81), computed through cofactors; like the
-// reference it REPLACES B by A - B so that the caller mixes f = A*r + B*(1-r)  (exp_ranF.c:1366-1368).
+// This is the reference's slcm (Ftools.c:39-81).  The 7-point cubic is ill-conditioned for a noticeable share of
+// random samples (a 1e-16 change of a coefficient moves F by 1e-9), and the DEGENSAC test downstream is
+// discontinuous in F, so the coefficients are accumulated in the reference's TERM ORDER: with -fmad=false they
+// round identically to the x86-64 build.  Like the reference it REPLACES B by A - B afterwards, so that the
+// caller mixes f = A*r + B*(1-r)  (exp_ranF.c:1366-1368).
 DG_HDN void seven_pt_cubic(const double* A, double* B, double* p) {
-  double C[9];
-  for (int i = 0; i < 9; ++i) C[i] = A[i] - B[i];
-  double cb[9], cc[9];
-  cb[0] = B[4] * B[8] - B[5] * B[7]; cb[1] = B[5] * B[6] - B[3] * B[8]; cb[2] = B[3] * B[7] - B[4] * B[6];
-  cb[3] = B[2] * B[7] - B[1] * B[8]; cb[4] = B[0] * B[8] - B[2] * B[6]; cb[5] = B[1] * B[6] - B[0] * B[7];
-  cb[6] = B[1] * B[5] - B[2] * B[4]; cb[7] = B[2] * B[3] - B[0] * B[5]; cb[8] = B[0] * B[4] - B[1] * B[3];
-  cc[0] = C[4] * C[8] - C[5] * C[7]; cc[1] = C[5] * C[6] - C[3] * C[8]; cc[2] = C[3] * C[7] - C[4] * C[6];
-  cc[3] = C[2] * C[7] - C[1] * C[8]; cc[4] = C[0] * C[8] - C[2] * C[6]; cc[5] = C[1] * C[6] - C[0] * C[7];
-  cc[6] = C[1] * C[5] - C[2] * C[4]; cc[7] = C[2] * C[3] - C[0] * C[5]; cc[8] = C[0] * C[4] - C[1] * C[3];
-  p[0] = B[0] * cb[0] + B[1] * cb[1] + B[2] * cb[2];
-  p[3] = C[0] * cc[0] + C[1] * cc[1] + C[2] * cc[2];
-  double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < 9; ++i) { s1 += cb[i] * C[i]; s2 += cc[i] * B[i]; }
-  p[1] = s1;
-  p[2] = s2;
-  for (int i = 0; i < 9; ++i) B[i] = C[i];
+  const double a11 = A[0], a12 = A[1], a13 = A[2], a21 = A[3], a22 = A[4], a23 = A[5], a31 = A[6], a32 = A[7], a33 = A[8];
+  double b11 = B[0], b12 = B[1], b13 = B[2], b21 = B[3], b22 = B[4], b23 = B[5], b31 = B[6], b32 = B[7], b33 = B[8];
+  p[0] = -(b13 * b22 * b31) + b12 * b23 * b31 + b13 * b21 * b32 - b11 * b23 * b32 - b12 * b21 * b33 + b11 * b22 * b33;
+  p[1] = -(a33 * b12 * b21) + a32 * b13 * b21 + a33 * b11 * b22 - a31 * b13 * b22 - a32 * b11 * b23 + a31 * b12 * b23 +
+         a23 * b12 * b31 - a22 * b13 * b31 - a13 * b22 * b31 + 3 * b13 * b22 * b31 + a12 * b23 * b31 -
+         3 * b12 * b23 * b31 - a23 * b11 * b32 + a21 * b13 * b32 + a13 * b21 * b32 - 3 * b13 * b21 * b32 -
+         a11 * b23 * b32 + 3 * b11 * b23 * b32 +
+         (a22 * b11 - a21 * b12 - a12 * b21 + 3 * b12 * b21 + a11 * b22 - 3 * b11 * b22) * b33;
+  p[2] = -(a21 * a33 * b12) + a21 * a32 * b13 + a13 * a32 * b21 - a12 * a33 * b21 + 2 * a33 * b12 * b21 -
+         2 * a32 * b13 * b21 - a13 * a31 * b22 + a11 * a33 * b22 - 2 * a33 * b11 * b22 + 2 * a31 * b13 * b22 +
+         a12 * a31 * b23 - a11 * a32 * b23 + 2 * a32 * b11 * b23 - 2 * a31 * b12 * b23 + 2 * a13 * b22 * b31 -
+         3 * b13 * b22 * b31 - 2 * a12 * b23 * b31 + 3 * b12 * b23 * b31 + a13 * a21 * b32 - 2 * a21 * b13 * b32 -
+         2 * a13 * b21 * b32 + 3 * b13 * b21 * b32 + 2 * a11 * b23 * b32 - 3 * b11 * b23 * b32 +
+         a23 * (-(a32 * b11) + a31 * b12 + a12 * b31 - 2 * b12 * b31 - a11 * b32 + 2 * b11 * b32) +
+         (-(a12 * a21) + 2 * a21 * b12 + 2 * a12 * b21 - 3 * b12 * b21 - 2 * a11 * b22 + 3 * b11 * b22) * b33 +
+         a22 * (a33 * b11 - a31 * b13 - a13 * b31 + 2 * b13 * b31 + a11 * b33 - 2 * b11 * b33);
+  for (int i = 0; i < 9; ++i) B[i] = A[i] - B[i];
+  b11 = B[0]; b12 = B[1]; b13 = B[2]; b21 = B[3]; b22 = B[4]; b23 = B[5]; b31 = B[6]; b32 = B[7]; b33 = B[8];
+  p[3] = -(b13 * b22 * b31) + b12 * b23 * b31 + b13 * b21 * b32 - b11 * b23 * b32 - b12 * b21 * b33 + b11 * b22 * b33;
 }
 
 // Real roots of po[0] x^3 + po[1] x^2 + po[2] x + po[3] (Cardano / trigonometric), the branch

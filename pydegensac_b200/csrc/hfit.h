@@ -12,6 +12,9 @@ namespace dg {
 //   h_from_4pt_u2h_quirk);  len > 4 : Hartley-normalised DLT, normal matrix by block reduction,
 //   smallest eigenvector (Jacobi instead of LAPACK dsyev_), de-normalisation.
 DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
+#ifdef DG_TRACE
+  fprintf(stderr, "u2h len=%d\n", len);
+#endif
   if (len < 4) return;
   if (len == 4) {
     DG_SYNC();
