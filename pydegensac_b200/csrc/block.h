@@ -65,6 +65,7 @@ DG_ENG inline double blk_sum(const Ctx& c, double v) {
   if (c.lane == 0) c.sc->red_d[c.wid] = v;
   DG_SYNC();
   double s = 0.0;
+  #pragma unroll 1
   for (int w = 0; w < c.nw; ++w) s += c.sc->red_d[w];
   return s;
 }
@@ -74,6 +75,7 @@ DG_ENG inline int blk_sum_i(const Ctx& c, int v) {
   if (c.lane == 0) c.sc->red_i[c.wid] = v;
   DG_SYNC();
   int s = 0;
+  #pragma unroll 1
   for (int w = 0; w < c.nw; ++w) s += c.sc->red_i[w];
   return s;
 }
@@ -84,6 +86,7 @@ DG_ENG inline int blk_excl_scan_i(const Ctx& c, int v, int* total) {
   if (c.lane == 31 || c.tid == c.nt - 1) c.sc->red_i[c.wid] = incl;
   DG_SYNC();
   int base = 0, tot = 0;
+  #pragma unroll 1
   for (int w = 0; w < c.nw; ++w) {
     const int t = c.sc->red_i[w];
     if (w < c.wid) base += t;
@@ -95,13 +98,16 @@ DG_ENG inline int blk_excl_scan_i(const Ctx& c, int v, int* total) {
 // k-wide vector sum (k <= kVecRed); result in c.sc->vec_out[0..k), visible to all threads on return.
 DG_ENGN void blk_sum_vec(const Ctx& c, double* v, int k) {
   DG_SYNC();
+  #pragma unroll 1
   for (int i = 0; i < k; ++i) {
     const double s = warp_sum(v[i]);
     if (c.lane == 0) c.sc->vec[c.wid * kVecRed + i] = s;
   }
   DG_SYNC();
+  #pragma unroll 1
   for (int i = c.tid; i < k; i += c.nt) {
     double s = 0.0;
+    #pragma unroll 1
     for (int w = 0; w < c.nw; ++w) s += c.sc->vec[w * kVecRed + i];
     c.sc->vec_out[i] = s;
   }
@@ -110,6 +116,7 @@ DG_ENGN void blk_sum_vec(const Ctx& c, double* v, int k) {
 // Broadcast n doubles computed by thread 0 (already stored in c.sc->bc) to every thread's `dst`.
 DG_ENG inline void bc_fetch(const Ctx& c, double* dst, int n) {
   DG_SYNC();
+  #pragma unroll 1
   for (int i = 0; i < n; ++i) dst[i] = c.sc->bc[i];
   DG_SYNC();
 }
@@ -123,13 +130,18 @@ DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list)
   const int end = (beg + per < c.N) ? beg + per : c.N;
   int cnt = 0;
   double J = 0.0;
+  // MSAC gain 1 - e/(9 th / 4) (reference truncQuad, rtools.c:228-236) with the division hoisted out of the loop
+  const double wq = th * 9 / 4;
+  const double winv = (th == 0) ? 0.0 : 1.0 / wq;
+  #pragma unroll 1
   for (int i = beg; i < end; ++i) {
     const double e = err[i];
-    J += trunc_quad(e, th);
+    if (th != 0 && e < wq) J += 1 - e * winv;
     if (e <= th) ++cnt;
   }
   int total;
   int off = blk_excl_scan_i(c, cnt, &total);
+  #pragma unroll 1
   for (int i = beg; i < end; ++i)
     if (err[i] <= th) list[off++] = i;
   Score s = make_score();
@@ -142,6 +154,7 @@ DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list)
 // count of err[i] < th (strict) or <= th over all points
 DG_ENG inline int blk_count_lt(const Ctx& c, const double* err, double th) {
   int cnt = 0;
+  #pragma unroll 1
   for (int i = c.tid; i < c.N; i += c.nt)
     if (err[i] < th) ++cnt;
   return blk_sum_i(c, cnt);

@@ -29,26 +29,34 @@ DG_HDN void h_from_F_3pts(const double* F, const double* u7, const int* tri, dou
   gkr_third_right_vector3(F, ec);  // column 2 of CCMATH's V (usually, not always, F ec = 0)
   const double Ex[9] = {0, -ec[2], ec[1], ec[2], 0, -ec[0], -ec[1], ec[0], 0};
   double A[9];  // A = [ec]x * F^T
+  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
+    #pragma unroll 1
     for (int j = 0; j < 3; ++j) {
       double s = 0.0;
+      #pragma unroll 1
       for (int k = 0; k < 3; ++k) s += Ex[3 * i + k] * F[3 * j + k];
       A[3 * i + j] = s;
     }
   double b[3], M[9];
+  #pragma unroll 1
   for (int t = 0; t < 3; ++t) {
     const double* p = u7 + 4 * tri[t];
     const double a1[3] = {p[0], p[1], 1.0};
     const double a2[3] = {p[2], p[3], 1.0};
     double Ab[3], p1[3], p2[3];
+    #pragma unroll 1
     for (int i = 0; i < 3; ++i) {
       double s = 0.0;
+      #pragma unroll 1
       for (int k = 0; k < 3; ++k) s += A[3 * i + k] * a2[k];
       Ab[i] = s;
     }
     cross3(p1, a1, Ab);
+    #pragma unroll 1
     for (int i = 0; i < 3; ++i) {
       double s = 0.0;
+      #pragma unroll 1
       for (int k = 0; k < 3; ++k) s += (-Ex[3 * i + k]) * a1[k];
       p2[i] = s;
     }
@@ -57,10 +65,14 @@ DG_HDN void h_from_F_3pts(const double* F, const double* u7, const int* tri, dou
   }
   const int sing = inv3(M);
   double v[3];
+  #pragma unroll 1
   for (int i = 0; i < 3; ++i) v[i] = M[3 * i] * b[0] + M[3 * i + 1] * b[1] + M[3 * i + 2] * b[2];
+  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
+    #pragma unroll 1
     for (int j = 0; j < 3; ++j) H[i + 3 * j] = A[3 * i + j] - ec[i] * v[j];
   if (isnan(H[0]) || isinf(H[0]) || sing) {
+    #pragma unroll 1
     for (int i = 0; i < 9; ++i) H[i] = 0.0;
     H[0] = H[4] = H[8] = 1.0;
   }
@@ -73,11 +85,14 @@ DG_ENGN void warp_h_fit_small(WarpScratch* ws, const double* u7, const int* idx,
   double A1[3] = {0, 0, 0}, A2[3] = {0, 0, 0};
   double* rows = ws->aux;   // 2*len x 9, len <= 6
   if (lane == 0) {
+    #pragma unroll 1
     for (int j = 0; j < len; ++j) {
       const double* p = u7 + 4 * idx[j];
       A1[1] += p[0]; A1[2] += p[1]; A2[1] += p[2]; A2[2] += p[3];
     }
+    #pragma unroll 1
     for (int i = 1; i < 3; ++i) { A1[i] /= len; A2[i] /= len; }
+    #pragma unroll 1
     for (int j = 0; j < len; ++j) {
       const double* p = u7 + 4 * idx[j];
       double a = p[0] - A1[1], b = p[1] - A1[2];
@@ -89,6 +104,7 @@ DG_ENGN void warp_h_fit_small(WarpScratch* ws, const double* u7, const int* idx,
     if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
     A1[1] *= -A1[0]; A1[2] *= -A1[0];
     A2[1] *= -A2[0]; A2[2] *= -A2[0];
+    #pragma unroll 1
     for (int j = 0; j < len; ++j) {
       const double* p = u7 + 4 * idx[j];
       double a[3], b[3];
@@ -96,6 +112,7 @@ DG_ENGN void warp_h_fit_small(WarpScratch* ws, const double* u7, const int* idx,
       b[0] = p[2] * A2[0] + A2[1]; b[1] = p[3] * A2[0] + A2[2]; b[2] = 1.0;
       double* r0 = rows + 18 * j;
       double* r1 = r0 + 9;
+      #pragma unroll 1
       for (int t = 0; t < 3; ++t) {
         r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
         r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
@@ -103,11 +120,13 @@ DG_ENGN void warp_h_fit_small(WarpScratch* ws, const double* u7, const int* idx,
     }
   }
   DG_WSYNC();
+  #pragma unroll 1
   for (int t = lane; t < 45; t += W) {
     int i = 0;
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
     const int jj = t - i * (i + 1) / 2;
     double s = 0.0;
+    #pragma unroll 1
     for (int r = 0; r < 2 * len; ++r) s += rows[9 * r + i] * rows[9 * r + jj];
     ws->A[9 * i + jj] = s;
     ws->A[9 * jj + i] = s;
@@ -117,8 +136,10 @@ DG_ENGN void warp_h_fit_small(WarpScratch* ws, const double* u7, const int* idx,
   DG_WSYNC();
   if (lane == 0) {
     int m = 0;
+    #pragma unroll 1
     for (int i = 1; i < 9; ++i)
       if (ws->A[i * 10] < ws->A[m * 10]) m = i;
+    #pragma unroll 1
     for (int i = 0; i < 9; ++i) h[i] = ws->V[i * 9 + m];
     denorm_H(h, A1, A2);
   }
@@ -136,19 +157,24 @@ DG_ENGN bool warp_checksample_triplet(WarpScratch* ws, const double* F, const do
 #ifdef DG_TRACE
     if (t == 0) {
       fprintf(stderr, "CSIN F=");
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) fprintf(stderr, "%.17g ", F[i]);
       fprintf(stderr, "u7=");
+      #pragma unroll 1
       for (int i = 0; i < 28; ++i) fprintf(stderr, "%.17g ", u7[i]);
       fprintf(stderr, "\n");
     }
     fprintf(stderr, "HDET t=%d H=%.10g %.10g %.10g %.10g\n", t, H[0], H[1], H[2], H[8]);
 #endif
     double Ds[7];
+    #pragma unroll 1
     for (int j = 0; j < 7; ++j) {
       Ds[j] = h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]);
       idx[j] = j;
     }
+    #pragma unroll 1
     for (int i = 0; i < 7; ++i)      // exchange sort of the reference's sortDs (DegUtils.c:164-183)
+      #pragma unroll 1
       for (int j = i + 1; j < 7; ++j)
         if (Ds[j] < Ds[i]) {
           const double td = Ds[j]; Ds[j] = Ds[i]; Ds[i] = td;
@@ -159,11 +185,13 @@ DG_ENGN bool warp_checksample_triplet(WarpScratch* ws, const double* F, const do
   warp_h_fit_small(ws, u7, idx, 5, H, lane, W);
   int cnt = 0;
   if (lane == 0)
+    #pragma unroll 1
     for (int j = 0; j < 7; ++j)
       if (h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]) < th) ++cnt;
 #ifdef DG_TRACE
   if (lane == 0) {
     double Ds[7];
+    #pragma unroll 1
     for (int j = 0; j < 7; ++j) Ds[j] = h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]);
     fprintf(stderr, "CS trip=%d cnt=%d Ds=%.6g %.6g %.6g %.6g %.6g %.6g %.6g H=%.10g %.10g %.10g\n", t, cnt, Ds[0], Ds[1], Ds[2], Ds[3], Ds[4], Ds[5], Ds[6], H[0] / H[8], H[1] / H[8], H[2] / H[8]);
   }
@@ -178,6 +206,7 @@ DG_ENGN bool blk_checksample(const Ctx& c, const double* F, const double* u7, do
   const int par = (c.nw >= 5) ? 5 : 1;
   const int W = DG_DEVICE_PASS ? 32 : 1;
   if (c.wid < par) {
+    #pragma unroll 1
     for (int t = c.wid; t < 5; t += par) {
       double Ht[9];
       const bool ok = warp_checksample_triplet(&c.sc->ws[c.wid], F, u7, t, th, Ht, c.lane, W);
@@ -190,10 +219,12 @@ DG_ENGN bool blk_checksample(const Ctx& c, const double* F, const double* u7, do
   }
   DG_SYNC();
   int win = -1;
+  #pragma unroll 1
   for (int t = 0; t < 5; ++t)
     if (c.sc->bci[t]) { win = t; break; }
   // the reference leaves the LAST tested triplet's H in the buffer when none succeeds; it is unused then
   const int src = win < 0 ? 4 : win;
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) H[i] = (src < 3) ? c.sc->bc[9 * src + i] : c.sc->vec[9 * (src - 3) + i];
   DG_SYNC();
   return win >= 0;
@@ -212,6 +243,7 @@ DG_ENGN Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** rows, in
   Score S = make_score(), Ss, maxS;
   maxS = blk_inlidxs(c, rows[e[4]], th, inl);
   if (maxS.I < 4) return S;
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) h[i] = Hio[i];
   if (maxS.I <= inlLimit) {
     blk_fit_H(c, inl, (int)maxS.I, h);
@@ -219,6 +251,7 @@ DG_ENGN Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** rows, in
     blk_randsubset(c, inl, (int)maxS.I, (int)inlLimit, cur);
     blk_fit_H(c, inl + maxS.I - inlLimit, (int)inlLimit, h);
   }
+  #pragma unroll 1
   for (int it = 0; it < kIlsqIters; ++it) {
     blk_resid_H_sampson(c, h, rows[d]);
     S = blk_inlidxs(c, rows[d], th, inl);
@@ -228,6 +261,7 @@ DG_ENGN Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** rows, in
       e[1] = e[0];
       e[0] = d;
       d = e[1];
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) Hio[i] = h[i];
     }
     if (Ss.I < 4) return maxS;
@@ -245,6 +279,7 @@ DG_ENGN Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** rows, in
     maxS = S;
     e[1] = e[0];
     e[0] = d;
+    #pragma unroll 1
     for (int i = 0; i < 9; ++i) Hio[i] = h[i];
   }
   return maxS;
@@ -268,7 +303,9 @@ DG_ENGN unsigned blk_inner_H(const Ctx& c, Workspace& W, double* H, double th, u
     if (ssiz > 12) ssiz = 12;
     int t = e[2]; e[2] = e[0]; e[0] = t;
     double h[9];
+    #pragma unroll 1
     for (int i = 0; i < 9; ++i) h[i] = H[i];
+    #pragma unroll 1
     for (int rep = 0; rep < kRanRep; ++rep) {
       blk_randsubset(c, inliers, ninl, ssiz, cur);
       blk_fit_H(c, inliers + ninl - ssiz, ssiz, h);
@@ -278,6 +315,7 @@ DG_ENGN unsigned blk_inner_H(const Ctx& c, Workspace& W, double* H, double th, u
       if (score_less(maxS, S)) {
         maxS = S;
         t = e[2]; e[2] = e[0]; e[0] = t;
+        #pragma unroll 1
         for (int i = 0; i < 9; ++i) H[i] = h[i];
       }
     }
@@ -285,6 +323,7 @@ DG_ENGN unsigned blk_inner_H(const Ctx& c, Workspace& W, double* H, double th, u
   }
   const double* d = rows[e[0]];
   int cnt = 0;
+  #pragma unroll 1
   for (int j = c.tid; j < c.N; j += c.nt) {
     const unsigned char m = (d[j] <= th) ? 1 : 0;
     mask[j] = m;
@@ -302,10 +341,12 @@ DG_ENGN int blk_compact(const Ctx& c, int n, int* list, Pred pred) {
   const int beg = c.tid * per;
   const int end = (beg + per < n) ? beg + per : n;
   int cnt = 0;
+  #pragma unroll 1
   for (int i = beg; i < end; ++i)
     if (pred(i)) ++cnt;
   int total;
   int off = blk_excl_scan_i(c, cnt, &total);
+  #pragma unroll 1
   for (int i = beg; i < end; ++i)
     if (pred(i)) list[off++] = i;
   DG_SYNC();
@@ -321,10 +362,12 @@ DG_ENGN unsigned blk_u2Fit(const Ctx& c, Workspace& W, double* F, unsigned char*
   const double dth = (ths - th) / (iters - 1);
   double* Ds = W.dtmp[5];
   int* inlI = W.itmp[3];
+  #pragma unroll 1
   for (unsigned iter = 0; iter < iters; ++iter) {
     blk_resid_F(c, F_SAMPSON, F, Ds);
     const double tcur = ths;
     int cnt = 0;
+    #pragma unroll 1
     for (int i = c.tid; i < c.N; i += c.nt) {
       const unsigned char m = (Ds[i] < tcur) ? 1 : 0;
       mask[i] = m;
@@ -339,6 +382,7 @@ DG_ENGN unsigned blk_u2Fit(const Ctx& c, Workspace& W, double* F, unsigned char*
   }
   blk_resid_F(c, F_SAMPSON, F, Ds);
   int cnt = 0;
+  #pragma unroll 1
   for (int i = c.tid; i < c.N; i += c.nt) {
     const unsigned char m = (Ds[i] < th) ? 1 : 0;
     mask[i] = m;
@@ -360,22 +404,28 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
   double* Ds = W.dtmp[5];
   int* usam = W.itmp[2];  // 10 indices
   unsigned max_i = 0, max_s = 0;
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) F[i] = 1.0;
+  #pragma unroll 1
   for (int i = c.tid; i < c.N; i += c.nt) inl[i] = 0;
   DG_SYNC();
+  #pragma unroll 1
   for (unsigned rep = 0; rep < 15; ++rep) {
     // dual_sample: fresh identity permutations, `pos <-> rand()%len` swaps (DegUtils.c:596-632)
     DG_SYNC();
     if (c.tid == 0) {
       DrawCursor t = cur;
       int tp[12], tv[12], nt;
+      #pragma unroll 1
       for (int side = 0; side < 2; ++side) {
         const int len = side ? nO : nH, s = side ? 4 : 6;
         const int* src = side ? uO : uH;
         nt = 0;
+        #pragma unroll 1
         for (int pos = 0; pos < s; ++pos) {
           const int idx = (int)(next_draw(t) % (uint32_t)len);
           int vp = pos, vi = idx;
+          #pragma unroll 1
           for (int q = 0; q < nt; ++q) { if (tp[q] == pos) vp = tv[q]; if (tp[q] == idx) vi = tv[q]; }
           int q = 0;
           while (q < nt && tp[q] != pos) ++q;
@@ -386,8 +436,10 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
           if (q == nt) { tp[nt] = idx; ++nt; }
           tv[q] = vp;
         }
+        #pragma unroll 1
         for (int pos = 0; pos < s; ++pos) {
           int vp = pos;
+          #pragma unroll 1
           for (int q = 0; q < nt; ++q) if (tp[q] == pos) vp = tv[q];
           usam[(side ? 6 : 0) + pos] = src[vp];
         }
@@ -399,6 +451,7 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
     blk_fit_F(c, usam, 10, nullptr, aF);
     blk_resid_F(c, F_SAMPSON, aF, Ds);
     int cnt = 0;
+    #pragma unroll 1
     for (int i = c.tid; i < c.N; i += c.nt) {
       const unsigned char m = (Ds[i] < th) ? 1 : 0;
       v[i] = m;
@@ -407,7 +460,9 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
     unsigned no_i = (unsigned)blk_sum_i(c, cnt);
     DG_SYNC();
     if (max_i < no_i) {
+      #pragma unroll 1
       for (int i = c.tid; i < c.N; i += c.nt) inl[i] = v[i];
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) F[i] = aF[i];
       max_i = no_i;
       DG_SYNC();
@@ -416,7 +471,9 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
       max_s = no_i;
       no_i = blk_u2Fit(c, W, aF, v, th, th * 3, 4);
       if (max_i < no_i) {
+        #pragma unroll 1
         for (int i = c.tid; i < c.N; i += c.nt) inl[i] = v[i];
+        #pragma unroll 1
         for (int i = 0; i < 9; ++i) F[i] = aF[i];
         max_i = no_i;
         DG_SYNC();
@@ -443,9 +500,12 @@ DG_HD void f_from_plane_parallax(const double* H, double ax1, double ay1, double
   ec[0] = ec[0] / n; ec[1] = ec[1] / n; ec[2] = ec[2] / n;
   const double S[9] = {0, -ec[2], ec[1], ec[2], 0, -ec[0], -ec[1], ec[0], 0};
   // Ht (row-major transpose of the column-major array, i.e. Ht[i][j] = H[j*3+i]); G = S * Ht ; F = G^T
+  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
+    #pragma unroll 1
     for (int j = 0; j < 3; ++j) {
       double s = 0.0;
+      #pragma unroll 1
       for (int k = 0; k < 3; ++k) s += S[3 * i + k] * H[j * 3 + k];
       F[3 * j + i] = s;
     }
@@ -465,12 +525,14 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
   int* uV = W.intbuff_best;   // ordered support of the current 2-point model
   int* ptr = W.itmp[0];       // persistent permutation over uN positions (innerH's list is dead here)
   blk_resid_H_sampson(c, H, Ds);
+  #pragma unroll 1
   for (int i = c.tid; i < c.N; i += c.nt) nhinl[i] = (Ds[i] > 100 * th) ? 1 : 0;
   DG_SYNC();
   const int nN = blk_compact(c, c.N, uN, [&](int i) { return nhinl[i] != 0; });
   const int nH = blk_compact(c, c.N, uHl, [&](int i) { return hinl[i] != 0; });
   unsigned max_i = 3, m_i = 4, max_sam = 10000, maxni = 0;
   if (nN < 4 || nH < 6) return 0;
+  #pragma unroll 1
   for (int i = c.tid; i < nN; i += c.nt) ptr[i] = i;
   DG_SYNC();
   const double th2 = th * 2;
@@ -486,7 +548,9 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
     DG_SYNC();
     if (c.tid == 0) {
       DrawCursor t = cur;
+      #pragma unroll 1
       for (int s = 0; s < nw; ++s) {
+        #pragma unroll 1
         for (int pos = 0; pos < 2; ++pos) {
           const int idx = pos + 1 + (int)(next_draw(t) % (uint32_t)(nN - pos - 1));
           const int a = ptr[pos]; ptr[pos] = ptr[idx]; ptr[idx] = a;
@@ -497,6 +561,7 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
     }
     DG_SYNC();
     // one warp per two-point hypothesis: support count over the off-plane correspondences
+    #pragma unroll 1
     for (int s = c.wid; s < nw; s += c.nw) {
       const int a = uN[pairs[2 * s]], b = uN[pairs[2 * s + 1]];
       double aF[9];
@@ -515,6 +580,7 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
     }
     DG_SYNC();
     int ev = -1;
+    #pragma unroll 1
     for (int s = 0; s < nw; ++s)
       if ((unsigned)counts[s] > m_i) { ev = s; break; }
     if (ev < 0) {
@@ -528,9 +594,13 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
       DrawCursor t = cur;
       t.j += 2u * (uint32_t)(ev + 1);
       int idxs[2 * 128];
+      #pragma unroll 1
       for (int s = ev + 1; s < nw; ++s)
+        #pragma unroll 1
         for (int pos = 0; pos < 2; ++pos) idxs[2 * s + pos] = pos + 1 + (int)(next_draw(t) % (uint32_t)(nN - pos - 1));
+      #pragma unroll 1
       for (int s = nw - 1; s > ev; --s)
+        #pragma unroll 1
         for (int pos = 1; pos >= 0; --pos) {
           const int idx = idxs[2 * s + pos];
           const int a = ptr[pos]; ptr[pos] = ptr[idx]; ptr[idx] = a;
@@ -549,12 +619,14 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
         return f_resid_sampson(aF, c.x1[p], c.y1[p], c.x2[p], c.y2[p]) < th2;
       });
       // uV currently holds POSITIONS in uN; convert to correspondence indices
+      #pragma unroll 1
       for (int i = c.tid; i < no_i; i += c.nt) uV[i] = uN[uV[i]];
       DG_SYNC();
       m_i = (unsigned)no_i;
       double Fnew[9];
       blk_inner_FH(c, W, uHl, nH, uV, no_i, th, Fnew, inl, cur);
       int cnt = 0, cnt2 = 0;
+      #pragma unroll 1
       for (int i = c.tid; i < c.N; i += c.nt) {
         if (inl[i]) { ++cnt; if (nhinl[i]) ++cnt2; }
       }
@@ -562,6 +634,7 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
       const unsigned both = (unsigned)blk_sum_i(c, cnt2);
       if (ninl > max_i) {
         max_i = ninl;
+        #pragma unroll 1
         for (int i = 0; i < 9; ++i) F[i] = Fnew[i];
         maxni = both;
         const unsigned ns = (unsigned)nsamples((int)maxni, nN, 2, 0.999);

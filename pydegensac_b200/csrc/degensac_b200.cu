@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/degensac_b200.h"
@@ -25,8 +26,28 @@ __device__ unsigned long long g_dg_prof[32];
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kMaxThreads = 256;
 constexpr int kChunk = 512;
+
+// CTA shape.  The replay phase is a latency chain (LO, DEGENSAC), so throughput comes from keeping MANY pairs in
+// flight per SM: small CTAs (default 64 threads) with the FP64 correspondences in the per-CTA global slab
+// (L1/L2 resident) instead of a 64 KB shared-memory tile.  DGB200_THREADS / DGB200_SMEM_TILE override for experiments.
+int cfg_threads() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DGB200_THREADS");
+    v = e ? atoi(e) : 64;
+    if (v < 32) v = 32;
+    if (v > kMaxThreads) v = kMaxThreads;
+    v = (v / 32) * 32;
+  }
+  return v;
+}
+int cfg_smem_tile() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DGB200_SMEM_TILE"); v = e ? atoi(e) : 0; }
+  return v;
+}
 
 struct BatchArgs {
   const double* x1y1;
@@ -46,7 +67,7 @@ struct BatchArgs {
 };
 
 template <int KIND>  // 0: fundamental matrix, 1: homography
-__global__ void __launch_bounds__(kThreads, 2) ransac_pairs_kernel(BatchArgs a) {
+__global__ void __launch_bounds__(kMaxThreads, 2) ransac_pairs_kernel(BatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_pair;
   dg::BlockScratch* sc = reinterpret_cast<dg::BlockScratch*>(smem_raw);
@@ -173,8 +194,9 @@ int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, doub
   const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128);
   const size_t tile = dg::align_up(sizeof(double) * (size_t)n, 128) * 4;
   size_t smem = sc_bytes + tile;
-  a.pts_in_smem = 1;
-  if (smem > g_c.smem_optin) { smem = sc_bytes; a.pts_in_smem = 0; }
+  a.pts_in_smem = cfg_smem_tile() ? 1 : 0;
+  if (!a.pts_in_smem || smem > g_c.smem_optin) { smem = sc_bytes; a.pts_in_smem = 0; }
+  const int kThreads = cfg_threads();
   auto kern = ransac_pairs_kernel<KIND>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;

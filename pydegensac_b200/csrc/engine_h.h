@@ -36,6 +36,7 @@ DG_ENGN unsigned blk_sym_count_H(const Ctx& c, const double* h, const int* list,
   HSym s;
   h_sym_prepare(h, &s);
   int cnt = 0;
+  #pragma unroll 1
   for (int j = c.tid; j < n; j += c.nt) {
     const int i = list[j];
     if (h_resid_symmax_gate(s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]) <= sym_th) ++cnt;
@@ -49,6 +50,7 @@ DG_ENGN bool hash_seen_elsewhere_h(const Ctx& c, Workspace& W, HashTab& ht, cons
   if (c.tid == 0) {
     const uint32_t h = superfasthash_i32(list, n);
     int same = 0, other = 0;
+    #pragma unroll 1
     for (int i = 0; i < ht.n; ++i)
       if (W.hhash[i] == h && W.hlen[i] == n) { if (W.hid[i] == iterID) same = 1; else other = 1; }
     int verdict = 0;
@@ -77,8 +79,10 @@ DG_ENGN Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, in
 #endif
   if (maxS.I < 4) return S;
   S = blk_inlidxs(c, W.err[e[4]], th * kMWM, inl);
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) h[i] = Hio[i];
   blk_fit_H(c, inl, (int)S.I, h);
+  #pragma unroll 1
   for (int it = 0; it < kIlsqIters; ++it) {
     blk_resid_H(c, P.metric, h, W.err[d]);
     Ss = blk_inlidxs(c, W.err[d], th, inl);
@@ -92,6 +96,7 @@ DG_ENGN Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, in
       e[1] = e[0];
       e[0] = d;
       d = e[1];
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) Hio[i] = h[i];
     }
     if (S.I < 4) return maxS;
@@ -104,6 +109,7 @@ DG_ENGN Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, in
     maxS = S;
     e[1] = e[0];
     e[0] = d;
+    #pragma unroll 1
     for (int i = 0; i < 9; ++i) Hio[i] = h[i];
   }
   return maxS;
@@ -118,7 +124,9 @@ DG_ENGN Score lo_inner_H(const Ctx& c, const HParams& P, Workspace& W, int* e, i
   if (ssiz > 12) ssiz = 12;
   int t = e[2]; e[2] = e[0]; e[0] = t;
   double h[9];
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) h[i] = Hout[i];
+  #pragma unroll 1
   for (int rep = 0; rep < kRanRep; ++rep) {
     blk_randsubset(c, inliers, ninl, ssiz, cur);
     blk_fit_H(c, inliers + ninl - ssiz, ssiz, h);
@@ -129,6 +137,7 @@ DG_ENGN Score lo_inner_H(const Ctx& c, const HParams& P, Workspace& W, int* e, i
     if (score_less(maxS, S)) {
       maxS = S;
       t = e[2]; e[2] = e[0]; e[0] = t;
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) Hout[i] = h[i];
     }
   }
@@ -166,6 +175,7 @@ DG_ENGN bool run_lo_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, 
     if (do_update) {
       const int t = st.e[0]; st.e[0] = st.e[3]; st.e[3] = t;
       st.maxS = S;
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) st.H[i] = h[i];
       new_max = true;
     }
@@ -179,14 +189,17 @@ DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int k
   DG_SYNC();
   if (c.tid == 0) { c.sc->counter[0] = 0; c.sc->counter[1] = 0; }
   DG_SYNC();
+  #pragma unroll 1
   for (int k = kbeg + c.tid; k <= kend; k += c.nt) {
     int sel[4];
     minimal_sample<4>(P.seed, (uint32_t)k, c.N, sel);
     double sx1[4], sy1[4], sx2[4], sy2[4], px1[4], py1[4], px2[4], py2[4];
+    #pragma unroll 1
     for (int t = 0; t < 4; ++t) {
       const int p = sel[t];
       px1[t] = c.x1[p]; py1[t] = c.y1[p]; px2[t] = c.x2[p]; py2[t] = c.y2[p];
     }
+    #pragma unroll 1
     for (int t = 0; t < 4; ++t) { sx1[t] = px1[3 - t]; sy1[t] = py1[3 - t]; sx2[t] = px2[3 - t]; sy2[t] = py2[3 - t]; }
     if (!oriented_ok_H(sx1, sy1, sx2, sy2)) continue;
     double h[9];
@@ -195,6 +208,7 @@ DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int k
     const int slot = atomic_inc_shared(&c.sc->counter[0]);
     if (slot < W.cand_cap) {
       Cand& cd = W.cand[slot];
+      #pragma unroll 1
       for (int j = 0; j < 9; ++j) cd.f[j] = h[j];
       cd.k = k;
       cd.root = 0;
@@ -204,10 +218,12 @@ DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int k
   int ncand = c.sc->counter[0];
   if (ncand > W.cand_cap) ncand = W.cand_cap;
   const double w94 = P.th * 9 / 4;
+  #pragma unroll 1
   for (int ci = c.wid; ci < ncand; ci += c.nw) {
     bool keep = passall;
     if (!passall) {
       double h[9];
+      #pragma unroll 1
       for (int j = 0; j < 9; ++j) h[j] = W.cand[ci].f[j];
       HSym s;
       if (P.metric != H_SAMPSON) h_sym_prepare(h, &s);
@@ -231,6 +247,7 @@ DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int k
   DG_SYNC();
   const int npass = c.sc->counter[1];
   if (c.tid == 0) {
+    #pragma unroll 1
     for (int a = 1; a < npass; ++a) {
       const int v = W.pass[a];
       const int key = W.cand[v].k;
@@ -246,6 +263,7 @@ DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int k
 // REPLAY of one surviving iteration (exp_ranH.c:580-756).
 DG_ENGN void replay_iteration_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, int k, const Cand& cd) {
   double h[9];
+  #pragma unroll 1
   for (int j = 0; j < 9; ++j) h[j] = cd.f[j];
   st.cur.seed = P.seed; st.cur.k = (uint32_t)k; st.cur.j = 5;
   bool new_max = false, do_iterate;
@@ -261,6 +279,7 @@ DG_ENGN void replay_iteration_H(const Ctx& c, const HParams& P, Workspace& W, HS
     st.e[3] = d;
     st.maxS = S;
     new_max = true;
+    #pragma unroll 1
     for (int j = 0; j < 9; ++j) st.H[j] = h[j];
   }
   if (score_less(st.maxSs, S)) {
@@ -286,13 +305,17 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
                                  int* stats_out) {
   HState st;
   st.maxS = make_score(); st.maxSs = make_score();
+  #pragma unroll 1
   for (int i = 0; i < 4; ++i) st.e[i] = i;
   st.e[4] = 3;
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) st.H[i] = 0.0;
   st.max_sam = P.max_iters; st.iter_cnt = 0; st.iterID = 0; st.no_rej = 0;
   st.ht.n = 0;
   st.cur.seed = P.seed; st.cur.k = 0; st.cur.j = 1;
+  #pragma unroll 1
   for (int r = 0; r < 4; ++r)
+    #pragma unroll 1
     for (int j = c.tid; j < c.N; j += c.nt) W.err[r][j] = 0.0;
   DG_SYNC();
 
@@ -314,6 +337,7 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
     const double T = st.maxS.J < st.maxSs.J ? st.maxS.J : st.maxSs.J;
     const int npass = wave_H(c, P, W, k0 + 1, kend, T, passall);
     bool rewave = false;
+    #pragma unroll 1
     for (int pos = 0; pos < npass; ++pos) {
       const Cand& cd = W.cand[W.pass[pos]];
       const int k = cd.k;
@@ -333,17 +357,20 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
   // post-loop LO if none ran (exp_ranH.c:759-862)
   if (st.iter_cnt == 0) {
     double h[9];
+    #pragma unroll 1
     for (int i = 0; i < 9; ++i) h[i] = st.H[i];
     run_lo_H(c, P, W, st, h);
   }
 
   const double* d = W.err[st.e[3]];
+  #pragma unroll 1
   for (int j = c.tid; j < c.N; j += c.nt) mask_out[j] = (d[j] <= P.th) ? 1 : 0;
   DG_SYNC();
   if (P.do_sym) {
     const Score Sc = blk_inlidxs(c, d, P.th, W.itmp[0]);
     HSym s;
     h_sym_prepare(st.H, &s);
+    #pragma unroll 1
     for (int j = c.tid; j < (int)Sc.I; j += c.nt) {
       const int i = W.itmp[0][j];
       if (h_resid_symmax_gate(s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]) > P.sym_th) mask_out[i] = 0;
@@ -351,6 +378,7 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
     DG_SYNC();
   }
   if (c.tid == 0) {
+    #pragma unroll 1
     for (int i = 0; i < 9; ++i) H_out[i] = st.H[i];
     stats_out[0] = no_sam;
     stats_out[1] = st.iter_cnt;

@@ -49,6 +49,7 @@ DG_ENGN void blk_resid_F(const Ctx& c, int metric, const double* F, double* out)
   DG_SYNC();
 }
 DG_ENGN void blk_resid_w_F(const Ctx& c, int metric, const double* F, double* out, double* w) {
+  #pragma unroll 1
   for (int i = c.tid; i < c.N; i += c.nt) {
     double e, ww;
     f_resid_w(metric, F, c.x1[i], c.y1[i], c.x2[i], c.y2[i], &e, &ww);
@@ -60,6 +61,7 @@ DG_ENGN void blk_resid_w_F(const Ctx& c, int metric, const double* F, double* ou
 // symmetric-epipolar consistency count over an index list (gate at exp_ranF.c:1383-1392)
 DG_ENGN unsigned blk_sym_count_F(const Ctx& c, const double* F, const int* list, int n, double sym_th) {
   int cnt = 0;
+  #pragma unroll 1
   for (int j = c.tid; j < n; j += c.nt) {
     const int i = list[j];
     if (f_resid_symepi(F, c.x1[i], c.y1[i], c.x2[i], c.y2[i]) <= sym_th) ++cnt;
@@ -73,6 +75,7 @@ DG_ENGN void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCu
   DG_SYNC();
   if (c.tid == 0) {
     DrawCursor t = cur;
+    #pragma unroll 1
     for (int i = 0; i < siz; ++i) {
       const int s = (int)(next_draw(t) % (uint32_t)(max_sz - i));
       const int j = max_sz - i - 1;
@@ -101,16 +104,20 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
     if (c.wid == 0) {   // warp 0: one lane per column of the 9 x len system, Householder QR across the lanes
       WarpScratch* ws = &c.sc->ws[0];
       const int W = DG_DEVICE_PASS ? 32 : 1;
+      #pragma unroll 1
       for (int i = c.lane; i < len; i += W) {
         const int p = idx[i];
         double row[9];
         f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], row);
+        #pragma unroll 1
         for (int r = 0; r < 9; ++r) ws->A[r * len + i] = row[r];
       }
       DG_WSYNC();
       if (w) {
+        #pragma unroll 1
         for (int i = c.lane; i < len; i += W) {
           const double wi = w[idx[i]];
+          #pragma unroll 1
           for (int t = 0; t < 9; ++t) {
             const int lin = i + 9 * t;
             if (lin < 9 * len) ws->A[lin] *= wi;
@@ -121,8 +128,10 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
       if (len > 0) warp_left_null_9xk(ws, len, c.lane, W);
       if (c.lane == 0) {
         double q[9];
+        #pragma unroll 1
         for (int i = 0; i < 9; ++i) q[i] = (len > 0) ? ws->cs[i] : ((i == 8) ? 1.0 : 0.0);
         enforce_rank2(q);
+        #pragma unroll 1
         for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
       }
     }
@@ -131,9 +140,91 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
     return;
   }
   DG_PROF_BEGIN(8);
+  if (len <= 32) {
+    // Small support (the 9..14-point inner LO samples, 10-point plane+parallax samples): the whole fit runs
+    // inside warp 0 -- one lane per correspondence, no block-wide reduction, rows kept in shared memory.
+    DG_SYNC();
+    if (c.wid == 0) {
+      const int W = DG_DEVICE_PASS ? 32 : 1;
+      WarpScratch* ws = &c.sc->ws[0];
+      double* rows = c.sc->vec;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      #pragma unroll 1
+      for (int j = c.lane; j < len; j += W) {
+        const int p = idx[j];
+        s0 += c.x1[p]; s1 += c.y1[p]; s2 += c.x2[p]; s3 += c.y2[p];
+      }
+      s0 = wl_sum(s0); s1 = wl_sum(s1); s2 = wl_sum(s2); s3 = wl_sum(s3);
+      double A1[3], A2[3];
+      A1[1] = s0 / len; A1[2] = s1 / len; A2[1] = s2 / len; A2[2] = s3 / len;
+      double d1 = 0.0, d2 = 0.0;
+      #pragma unroll 1
+      for (int j = c.lane; j < len; j += W) {
+        const int p = idx[j];
+        double a = c.x1[p] - A1[1], b = c.y1[p] - A1[2];
+        d1 += sqrt(a * a + b * b);
+        a = c.x2[p] - A2[1]; b = c.y2[p] - A2[2];
+        d2 += sqrt(a * a + b * b);
+      }
+      A1[0] = wl_sum(d1); A2[0] = wl_sum(d2);
+      if (A1[0] != 0) A1[0] = len * sqrt(2.0) / A1[0];
+      if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
+      A1[1] *= -A1[0]; A1[2] *= -A1[0];
+      A2[1] *= -A2[0]; A2[2] *= -A2[0];
+      #pragma unroll 1
+      for (int j = c.lane; j < len; j += W) {
+        const int p = idx[j];
+        double a[3], b[3];
+        a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
+        b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
+        const double ww = w ? w[p] : 1.0;
+        #pragma unroll 1
+        for (int k = 0; k < 3; ++k)
+          #pragma unroll 1
+          for (int l = 0; l < 3; ++l) {
+            double v = a[l] * b[k];
+            if (w) v *= ww;
+            rows[9 * j + 3 * k + l] = v;
+          }
+      }
+      DG_WSYNC();
+      #pragma unroll 1
+      for (int t = c.lane; t < 45; t += W) {
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= t) ++i;
+        const int jj = t - i * (i + 1) / 2;
+        double s = 0.0;
+        #pragma unroll 1
+        for (int r = 0; r < len; ++r) s += rows[9 * r + i] * rows[9 * r + jj];
+        ws->A[9 * i + jj] = s;
+        ws->A[9 * jj + i] = s;
+      }
+      DG_WSYNC();
+      warp_jacobi_eig9(ws, c.lane, W);
+      DG_WSYNC();
+      if (c.lane == 0) {
+        int m = 0;
+        #pragma unroll 1
+        for (int i = 1; i < 9; ++i)
+          if (ws->A[i * 10] < ws->A[m * 10]) m = i;
+        double q[9];
+        #pragma unroll 1
+        for (int i = 0; i < 9; ++i) q[i] = ws->V[i * 9 + m];
+        enforce_rank2(q);
+        denorm_F(q, A1, A2);
+        #pragma unroll 1
+        for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+      }
+    }
+    bc_fetch(c, f, 9);
+    DG_PROF_END(8);
+    return;
+  }
   // Hartley normalisation (reference normu, utools.c:7-51)
   double v[kVecRed];
+  #pragma unroll 1
   for (int i = 0; i < 4; ++i) v[i] = 0.0;
+  #pragma unroll 1
   for (int j = c.tid; j < len; j += c.nt) {
     const int p = idx[j];
     v[0] += c.x1[p]; v[1] += c.y1[p]; v[2] += c.x2[p]; v[3] += c.y2[p];
@@ -143,6 +234,7 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
   A1[1] = c.sc->vec_out[0] / len; A1[2] = c.sc->vec_out[1] / len;
   A2[1] = c.sc->vec_out[2] / len; A2[2] = c.sc->vec_out[3] / len;
   v[0] = 0.0; v[1] = 0.0;
+  #pragma unroll 1
   for (int j = c.tid; j < len; j += c.nt) {
     const int p = idx[j];
     double a = c.x1[p] - A1[1], b = c.y1[p] - A1[2];
@@ -157,18 +249,24 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
   A1[1] *= -A1[0]; A1[2] *= -A1[0];
   A2[1] *= -A2[0]; A2[2] *= -A2[0];
   // normal matrix of the normalised rows (reference lin_fmN + cov_mat, Ftools.c:300-328, utools.c:170-184)
+  #pragma unroll 1
   for (int i = 0; i < 45; ++i) v[i] = 0.0;
+  #pragma unroll 1
   for (int j = c.tid; j < len; j += c.nt) {
     const int p = idx[j];
     double a[3], b[3], row[9];
     a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
     b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
+    #pragma unroll 1
     for (int k = 0; k < 3; ++k)
+      #pragma unroll 1
       for (int l = 0; l < 3; ++l) row[3 * k + l] = a[l] * b[k];
     const double ww = w ? w[p] : 1.0;
     if (w) for (int k = 0; k < 9; ++k) row[k] *= ww;
     int t = 0;
+    #pragma unroll 1
     for (int i = 0; i < 9; ++i)
+      #pragma unroll 1
       for (int jj = 0; jj <= i; ++jj) v[t++] += row[i] * row[jj];
   }
   blk_sum_vec(c, v, 45);
@@ -177,9 +275,11 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
     warp_min_eigvec9_packed(ws, c.sc->vec_out, c.lane, DG_DEVICE_PASS ? 32 : 1);
     if (c.lane == 0) {
       double q[9];
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
       enforce_rank2(q);
       denorm_F(q, A1, A2);
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
     }
   }

@@ -20,18 +20,96 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
     DG_SYNC();
     if (c.tid == 0) {
       double px1[4], py1[4], px2[4], py2[4], hh[9];
+      #pragma unroll 1
       for (int i = 0; i < 4; ++i) {
         const int p = idx[i];
         px1[i] = c.x1[p]; py1[i] = c.y1[p]; px2[i] = c.x2[p]; py2[i] = c.y2[p];
       }
       h_from_4pt_u2h_quirk(px1, py1, px2, py2, hh);
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) c.sc->bc[i] = hh[i];
     }
     bc_fetch(c, h, 9);
     return;
   }
+  if (len <= 32) {   // small support: whole fit inside warp 0 (see blk_fit_F)
+    DG_SYNC();
+    if (c.wid == 0) {
+      const int W = DG_DEVICE_PASS ? 32 : 1;
+      WarpScratch* ws = &c.sc->ws[0];
+      double* rows = c.sc->vec;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      #pragma unroll 1
+      for (int j = c.lane; j < len; j += W) {
+        const int p = idx[j];
+        s0 += c.x1[p]; s1 += c.y1[p]; s2 += c.x2[p]; s3 += c.y2[p];
+      }
+      s0 = wl_sum(s0); s1 = wl_sum(s1); s2 = wl_sum(s2); s3 = wl_sum(s3);
+      double A1[3], A2[3];
+      A1[1] = s0 / len; A1[2] = s1 / len; A2[1] = s2 / len; A2[2] = s3 / len;
+      double d1 = 0.0, d2 = 0.0;
+      #pragma unroll 1
+      for (int j = c.lane; j < len; j += W) {
+        const int p = idx[j];
+        double a = c.x1[p] - A1[1], b = c.y1[p] - A1[2];
+        d1 += sqrt(a * a + b * b);
+        a = c.x2[p] - A2[1]; b = c.y2[p] - A2[2];
+        d2 += sqrt(a * a + b * b);
+      }
+      A1[0] = wl_sum(d1); A2[0] = wl_sum(d2);
+      if (A1[0] != 0) A1[0] = len * sqrt(2.0) / A1[0];
+      if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
+      A1[1] *= -A1[0]; A1[2] *= -A1[0];
+      A2[1] *= -A2[0]; A2[2] *= -A2[0];
+      #pragma unroll 1
+      for (int j = c.lane; j < len; j += W) {
+        const int p = idx[j];
+        double a[3], b[3];
+        a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
+        b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
+        double* r0 = rows + 18 * j;
+        double* r1 = r0 + 9;
+        #pragma unroll 1
+        for (int t = 0; t < 3; ++t) {
+          r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
+          r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
+        }
+      }
+      DG_WSYNC();
+      #pragma unroll 1
+      for (int t = c.lane; t < 45; t += W) {
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= t) ++i;
+        const int jj = t - i * (i + 1) / 2;
+        double s = 0.0;
+        #pragma unroll 1
+        for (int r = 0; r < 2 * len; ++r) s += rows[9 * r + i] * rows[9 * r + jj];
+        ws->A[9 * i + jj] = s;
+        ws->A[9 * jj + i] = s;
+      }
+      DG_WSYNC();
+      warp_jacobi_eig9(ws, c.lane, W);
+      DG_WSYNC();
+      if (c.lane == 0) {
+        int m = 0;
+        #pragma unroll 1
+        for (int i = 1; i < 9; ++i)
+          if (ws->A[i * 10] < ws->A[m * 10]) m = i;
+        double q[9];
+        #pragma unroll 1
+        for (int i = 0; i < 9; ++i) q[i] = ws->V[i * 9 + m];
+        denorm_H(q, A1, A2);
+        #pragma unroll 1
+        for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
+      }
+    }
+    bc_fetch(c, h, 9);
+    return;
+  }
   double v[kVecRed];
+  #pragma unroll 1
   for (int i = 0; i < 4; ++i) v[i] = 0.0;
+  #pragma unroll 1
   for (int j = c.tid; j < len; j += c.nt) {
     const int p = idx[j];
     v[0] += c.x1[p]; v[1] += c.y1[p]; v[2] += c.x2[p]; v[3] += c.y2[p];
@@ -41,6 +119,7 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
   A1[1] = c.sc->vec_out[0] / len; A1[2] = c.sc->vec_out[1] / len;
   A2[1] = c.sc->vec_out[2] / len; A2[2] = c.sc->vec_out[3] / len;
   v[0] = 0.0; v[1] = 0.0;
+  #pragma unroll 1
   for (int j = c.tid; j < len; j += c.nt) {
     const int p = idx[j];
     double a = c.x1[p] - A1[1], b = c.y1[p] - A1[2];
@@ -54,18 +133,23 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
   if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
   A1[1] *= -A1[0]; A1[2] *= -A1[0];
   A2[1] *= -A2[0]; A2[2] *= -A2[0];
+  #pragma unroll 1
   for (int i = 0; i < 45; ++i) v[i] = 0.0;
+  #pragma unroll 1
   for (int j = c.tid; j < len; j += c.nt) {
     const int p = idx[j];
     double a[3], b[3], r0[9], r1[9];
     a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
     b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
+    #pragma unroll 1
     for (int t = 0; t < 3; ++t) {  // reference lin_hgN, Htools.c:60-99
       r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
       r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
     }
     int t = 0;
+    #pragma unroll 1
     for (int i = 0; i < 9; ++i)
+      #pragma unroll 1
       for (int jj = 0; jj <= i; ++jj) {
         v[t] += r0[i] * r0[jj];
         v[t] += r1[i] * r1[jj];
@@ -78,8 +162,10 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
     warp_min_eigvec9_packed(ws, c.sc->vec_out, c.lane, DG_DEVICE_PASS ? 32 : 1);
     if (c.lane == 0) {
       double q[9];
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
       denorm_H(q, A1, A2);
+      #pragma unroll 1
       for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
     }
   }

@@ -16,20 +16,24 @@ DG_HDN int nullspace9(double* M, double* ns) {
   const double tol = 1e-12;
   int freec[9], pivc[9];
   int nfree = 0, npiv = 0, row = 0;
+  #pragma unroll 1
   for (int col = 0; col < 9; ++col) {
     int best = row;
     double mag = fabs(M[9 * row + col]);
+    #pragma unroll 1
     for (int r = row + 1; r < 9; ++r) {
       const double t = fabs(M[9 * r + col]);
       if (mag < t) { mag = t; best = r; }
     }
     if (mag < tol) {
       freec[nfree++] = col;
+      #pragma unroll 1
       for (int r = row; r < 9; ++r) M[9 * r + col] = 0.0;
       continue;
     }
     pivc[npiv++] = col;
     if (best != row) {
+      #pragma unroll 1
       for (int c = col; c < 9; ++c) {
         const double t = M[9 * row + c];
         M[9 * row + c] = M[9 * best + c];
@@ -37,17 +41,23 @@ DG_HDN int nullspace9(double* M, double* ns) {
       }
     }
     const double p = M[9 * row + col];
+    #pragma unroll 1
     for (int c = col; c < 9; ++c) M[9 * row + c] /= p;
+    #pragma unroll 1
     for (int r = 0; r < 9; ++r) {
       if (r == row) continue;
       const double a = M[9 * r + col];
+      #pragma unroll 1
       for (int c = col; c < 9; ++c) M[9 * r + c] -= a * M[9 * row + c];
     }
     ++row;
   }
+  #pragma unroll 1
   for (int k = 0; k < nfree; ++k) {
     const int j = freec[k];
+    #pragma unroll 1
     for (int l = 0; l < npiv; ++l) ns[k * 9 + pivc[l]] = -M[l * 9 + j];
+    #pragma unroll 1
     for (int l = 0; l < nfree; ++l) ns[k * 9 + freec[l]] = (j == freec[l]) ? 1.0 : 0.0;
   }
   return nfree;
@@ -59,16 +69,23 @@ DG_HDN int nullspace9(double* M, double* ns) {
 // V (V[r*9+k]) is the eigenvector of d[k].  Eigenvalues are NOT sorted; callers pick the minimum.
 // ---------------------------------------------------------------------------------------------
 DG_HDN void jacobi_eig9(double* A, double* V, double* d) {
+  #pragma unroll 1
   for (int i = 0; i < 81; ++i) V[i] = 0.0;
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) V[i * 10] = 1.0;
+  #pragma unroll 1
   for (int sweep = 0; sweep < 40; ++sweep) {
     double off = 0.0, dia = 0.0;
+    #pragma unroll 1
     for (int p = 0; p < 9; ++p) {
       dia += A[p * 10] * A[p * 10];
+      #pragma unroll 1
       for (int q = p + 1; q < 9; ++q) off += A[p * 9 + q] * A[p * 9 + q];
     }
     if (!(off > 4e-30 * dia) || off == 0.0) break;  // off-norm at rounding level: converged
+    #pragma unroll 1
     for (int p = 0; p < 8; ++p) {
+      #pragma unroll 1
       for (int q = p + 1; q < 9; ++q) {
         const double apq = A[p * 9 + q];
         if (apq == 0.0) continue;
@@ -76,16 +93,19 @@ DG_HDN void jacobi_eig9(double* A, double* V, double* d) {
         const double theta = (aqq - app) / (2.0 * apq);
         const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
         const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        #pragma unroll 1
         for (int k = 0; k < 9; ++k) {  // columns p,q
           const double akp = A[k * 9 + p], akq = A[k * 9 + q];
           A[k * 9 + p] = c * akp - s * akq;
           A[k * 9 + q] = s * akp + c * akq;
         }
+        #pragma unroll 1
         for (int k = 0; k < 9; ++k) {  // rows p,q
           const double apk = A[p * 9 + k], aqk = A[q * 9 + k];
           A[p * 9 + k] = c * apk - s * aqk;
           A[q * 9 + k] = s * apk + c * aqk;
         }
+        #pragma unroll 1
         for (int k = 0; k < 9; ++k) {
           const double vkp = V[k * 9 + p], vkq = V[k * 9 + q];
           V[k * 9 + p] = c * vkp - s * vkq;
@@ -94,6 +114,7 @@ DG_HDN void jacobi_eig9(double* A, double* V, double* d) {
       }
     }
   }
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) d[i] = A[i * 10];
 }
 
@@ -102,8 +123,10 @@ DG_HDN void min_eigvec9(double* C, double* v) {
   double V[81], d[9];
   jacobi_eig9(C, V, d);
   int j = 0;
+  #pragma unroll 1
   for (int i = 1; i < 9; ++i)
     if (d[i] < d[j]) j = i;
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) v[i] = V[i * 9 + j];
 }
 
@@ -113,13 +136,18 @@ DG_HDN void min_eigvec9(double* C, double* v) {
 // Ftools.c:330-347, LAPACK dgesvd_) and for the epipole in Hdetect (DegUtils.c:109, CCMATH svduv).
 // ---------------------------------------------------------------------------------------------
 DG_HDN void svd3_onesided(const double* A, double* G, double* V, double* sv) {
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) { G[i] = A[i]; V[i] = 0.0; }
   V[0] = V[4] = V[8] = 1.0;
+  #pragma unroll 1
   for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
+    #pragma unroll 1
     for (int p = 0; p < 2; ++p) {
+      #pragma unroll 1
       for (int q = p + 1; q < 3; ++q) {
         double al = 0.0, be = 0.0, ga = 0.0;
+        #pragma unroll 1
         for (int i = 0; i < 3; ++i) {
           al += G[3 * i + p] * G[3 * i + p];
           be += G[3 * i + q] * G[3 * i + q];
@@ -130,6 +158,7 @@ DG_HDN void svd3_onesided(const double* A, double* G, double* V, double* sv) {
         const double zeta = (be - al) / (2.0 * ga);
         const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
         const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        #pragma unroll 1
         for (int i = 0; i < 3; ++i) {
           const double gp = G[3 * i + p], gq = G[3 * i + q];
           G[3 * i + p] = c * gp - s * gq;
@@ -142,6 +171,7 @@ DG_HDN void svd3_onesided(const double* A, double* G, double* V, double* sv) {
     }
     if (!rotated) break;
   }
+  #pragma unroll 1
   for (int c = 0; c < 3; ++c) sv[c] = sqrt(G[c] * G[c] + G[3 + c] * G[3 + c] + G[6 + c] * G[6 + c]);
 }
 
@@ -152,7 +182,9 @@ DG_HDN void enforce_rank2(double* F) {
   int m = 0;
   if (sv[1] < sv[m]) m = 1;
   if (sv[2] < sv[m]) m = 2;
+  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
+    #pragma unroll 1
     for (int j = 0; j < 3; ++j) F[3 * i + j] -= G[3 * i + m] * V[3 * j + m];
 }
 
@@ -176,6 +208,7 @@ DG_HDN void right_null3(const double* A, double* v) {
 // ---------------------------------------------------------------------------------------------
 DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
   double a[9], d[3], e[2], V[9];
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) a[i] = Ain[i];
   e[0] = e[1] = 0.0;
   // --- column 0 reflector
@@ -188,6 +221,7 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
       s += a[0] * h;
       s = 1. / s;
       w0 += h;
+      #pragma unroll 1
       for (int k = 1; k < 3; ++k) {
         double r = w0 * a[k] + w1 * a[3 + k] + w2 * a[6 + k];
         r *= s;
@@ -208,6 +242,7 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
       s = 1. / s;
       const double p0 = a[1] + h;
       const double t = 1. / p0;
+      #pragma unroll 1
       for (int row = 1; row < 3; ++row) {
         double r = p0 * a[3 * row + 1] + a[2] * a[3 * row + 2];
         r *= s;
@@ -236,6 +271,7 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
   }
   e[1] = a[5];
   d[2] = a[8];
+  #pragma unroll 1
   for (int i = 0; i < 9; ++i) V[i] = 0.0;
   V[0] = 1.0; V[4] = 1.0; V[8] = 1.0;
   if (hb != 0.) {
@@ -248,17 +284,21 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
   // --- implicit-shift QR sweeps on the bidiagonal (d,e)
   int m = 3;
   double t = fabs(d[0]);
+  #pragma unroll 1
   for (int j = 1; j < 3; ++j) {
     const double s = fabs(d[j]) + fabs(e[j - 1]);
     if (s > t) t = s;
   }
   t *= 1.e-15;
+  #pragma unroll 1
   for (int it = 0; m > 1 && it < 300; ++it) {
     int k;
+    #pragma unroll 1
     for (k = m - 1; k > 0; --k) {
       if (fabs(e[k - 1]) < t) break;
       if (fabs(d[k - 1]) < t) {
         double s = 1., c = 0.;
+        #pragma unroll 1
         for (int i = k; i < m; ++i) {
           const double aa = s * e[i - 1], bb = d[i];
           e[i - 1] *= c;
@@ -276,6 +316,7 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
     if (u != 0.) {
       double c = sqrt((u + aa) / (u + u));
       if (c != 0.) s /= (c * u); else s = 1.;
+      #pragma unroll 1
       for (int i = k; i < m - 1; ++i) {
         bb = e[i];
         if (i > k) {
@@ -287,6 +328,7 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
         }
         aa = c * y + s * bb;
         bb = c * bb - s * y;
+        #pragma unroll 1
         for (int r = 0; r < 3; ++r) {
           const double w = c * V[3 * r + i] + s * V[3 * r + i + 1];
           V[3 * r + i + 1] = c * V[3 * r + i + 1] - s * V[3 * r + i];
@@ -317,32 +359,44 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
 DG_HDN void left_null_9xk(double* Z, int len, double* q) {
   double vs[8][9];
   double beta[8];
+  #pragma unroll 1
   for (int c = 0; c < len; ++c) {
     double nrm = 0.0;
+    #pragma unroll 1
     for (int r = c; r < 9; ++r) nrm += Z[r * len + c] * Z[r * len + c];
     nrm = sqrt(nrm);
+    #pragma unroll 1
     for (int r = 0; r < 9; ++r) vs[c][r] = 0.0;
     if (nrm == 0.0) { beta[c] = 0.0; continue; }
     const double x0 = Z[c * len + c];
     const double alpha = (x0 >= 0.0) ? -nrm : nrm;
+    #pragma unroll 1
     for (int r = c; r < 9; ++r) vs[c][r] = Z[r * len + c];
     vs[c][c] = x0 - alpha;
     double vn = 0.0;
+    #pragma unroll 1
     for (int r = c; r < 9; ++r) vn += vs[c][r] * vs[c][r];
     beta[c] = (vn > 0.0) ? 2.0 / vn : 0.0;
+    #pragma unroll 1
     for (int cc = c; cc < len; ++cc) {
       double dot = 0.0;
+      #pragma unroll 1
       for (int r = c; r < 9; ++r) dot += vs[c][r] * Z[r * len + cc];
       dot *= beta[c];
+      #pragma unroll 1
       for (int r = c; r < 9; ++r) Z[r * len + cc] -= dot * vs[c][r];
     }
   }
+  #pragma unroll 1
   for (int r = 0; r < 9; ++r) q[r] = 0.0;
   q[8] = 1.0;
+  #pragma unroll 1
   for (int c = len - 1; c >= 0; --c) {
     double dot = 0.0;
+    #pragma unroll 1
     for (int r = c; r < 9; ++r) dot += vs[c][r] * q[r];
     dot *= beta[c];
+    #pragma unroll 1
     for (int r = c; r < 9; ++r) q[r] -= dot * vs[c][r];
   }
 }
@@ -352,12 +406,16 @@ DG_HDN void left_null_9xk(double* Z, int len, double* q) {
 // matutls/minv.c:11,27), in which case the matrix content is unspecified.
 DG_HDN int inv3(double* a) {
   double m[3][6];
+  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
+    #pragma unroll 1
     for (int j = 0; j < 3; ++j) { m[i][j] = a[3 * i + j]; m[i][3 + j] = (i == j) ? 1.0 : 0.0; }
   double tq = 0.0;
+  #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
     int best = c;
     double s = fabs(m[c][c]);
+    #pragma unroll 1
     for (int r = c + 1; r < 3; ++r) {
       const double t = fabs(m[r][c]);
       if (t > s) { s = t; best = r; }
@@ -365,16 +423,22 @@ DG_HDN int inv3(double* a) {
     tq = tq > s ? tq : s;
     if (s < 1e-15 * tq || s == 0.0) return -1;
     if (best != c)
+      #pragma unroll 1
       for (int k = 0; k < 6; ++k) { const double t = m[c][k]; m[c][k] = m[best][k]; m[best][k] = t; }
     const double inv = 1.0 / m[c][c];
+    #pragma unroll 1
     for (int k = 0; k < 6; ++k) m[c][k] *= inv;
+    #pragma unroll 1
     for (int r = 0; r < 3; ++r) {
       if (r == c) continue;
       const double f = m[r][c];
+      #pragma unroll 1
       for (int k = 0; k < 6; ++k) m[r][k] -= f * m[c][k];
     }
   }
+  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
+    #pragma unroll 1
     for (int j = 0; j < 3; ++j) a[3 * i + j] = m[i][3 + j];
   return 0;
 }
@@ -415,6 +479,7 @@ DG_HD uint32_t sfh_final(uint32_t hash) {
 DG_HD uint32_t superfasthash_i32(const int* idx, int n) {
   if (n <= 0) return 0u;
   uint32_t h = sfh_init(n);
+  #pragma unroll 1
   for (int i = 0; i < n; ++i) h = sfh_word(h, (uint32_t)idx[i]);
   return sfh_final(h);
 }
@@ -422,6 +487,7 @@ DG_HD uint32_t superfasthash_i32(const int* idx, int n) {
 // Number of samples for a confidence level (reference nsamples, rtools.c:202-225).
 DG_HD int nsamples(int ninl, int ptNum, int samsiz, double conf) {
   double a = 1.0, b = 1.0;
+  #pragma unroll 1
   for (int i = 0; i < samsiz; ++i) {
     a *= ninl - i;
     b *= ptNum - i;

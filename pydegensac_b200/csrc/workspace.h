@@ -29,14 +29,18 @@ DG_HD void workspace_carve(unsigned char* base, int N, int chunk, Workspace* W, 
   const size_t rowd = align_up(sizeof(double) * (size_t)N, 128);
   const size_t rowi = align_up(sizeof(int) * (size_t)(N + kListPad), 128);
   const size_t rowb = align_up((size_t)N, 128);
+  #pragma unroll 1
   for (int i = 0; i < 4; ++i) { W->err[i] = (double*)p; p += rowd; }
   W->errBest = (double*)p; p += rowd;
   W->w = (double*)p; p += rowd;
+  #pragma unroll 1
   for (int i = 0; i < 8; ++i) { W->dtmp[i] = (double*)p; p += rowd; }
   W->inliers = (int*)p; p += rowi;
   W->intbuff = (int*)p; p += rowi;
   W->intbuff_best = (int*)p; p += rowi;
+  #pragma unroll 1
   for (int i = 0; i < 4; ++i) { W->itmp[i] = (int*)p; p += rowi; }
+  #pragma unroll 1
   for (int i = 0; i < 4; ++i) { W->btmp[i] = p; p += rowb; }
   W->cand = (Cand*)p; p += align_up(sizeof(Cand) * (size_t)(3 * chunk), 128);
   W->pass = (int*)p; p += align_up(sizeof(int) * (size_t)(3 * chunk), 128);
