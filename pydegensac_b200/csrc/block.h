@@ -24,11 +24,13 @@ struct BlockScratch {
   WarpScratch ws[5];               // per-warp tiles for the cooperative 9x9 solves (5 = checksample triplets)
 };
 
+struct Tile32;
 struct Ctx {
   int tid, nt, lane, wid, nw;
   int N;
   const double* x1; const double* y1; const double* x2; const double* y2;   // SoA correspondences
   BlockScratch* sc;
+  const Tile32* t32;   // FP32 upper-bound filter tile (nullptr: the wave scores in FP64)
 };
 
 #if DG_DEVICE_PASS

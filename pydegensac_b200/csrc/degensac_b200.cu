@@ -18,6 +18,7 @@
 #include "../../include/degensac_b200.h"
 #include "engine_f.h"
 #include "engine_h.h"
+#include "filter32.h"
 #include "workspace.h"
 
 #ifdef DG_PROF
@@ -64,6 +65,7 @@ struct BatchArgs {
   int chunk;
   int* work_counter;
   int pts_in_smem;
+  int tile32_in_smem;   // FP32 filter tile placement (F path)
 };
 
 template <int KIND>  // 0: fundamental matrix, 1: homography
@@ -78,12 +80,18 @@ __global__ void __launch_bounds__(kMaxThreads, 2) ransac_pairs_kernel(BatchArgs 
   dg::workspace_carve(a.workspace + (size_t)blockIdx.x * a.ws_stride, n, a.chunk, &W, &soa_global);
   const size_t row = dg::align_up(sizeof(double) * (size_t)n, 128) / sizeof(double);
   double* soa = a.pts_in_smem ? reinterpret_cast<double*>(smem_raw + sc_bytes) : soa_global;
+  const size_t soa_smem_bytes = a.pts_in_smem ? dg::align_up(sizeof(double) * (size_t)n, 128) * 4 : 0;
+  dg::Pt32* tile32 = a.tile32_in_smem
+                         ? reinterpret_cast<dg::Pt32*>(smem_raw + sc_bytes + soa_smem_bytes)
+                         : reinterpret_cast<dg::Pt32*>(dg::workspace_tile32(a.workspace + (size_t)blockIdx.x * a.ws_stride, n, a.chunk));
+  dg::Tile32 t32;
 
   dg::Ctx c;
   c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5;
   c.N = n;
   c.x1 = soa; c.y1 = soa + row; c.x2 = soa + 2 * row; c.y2 = soa + 3 * row;
   c.sc = sc;
+  c.t32 = nullptr;
 
   for (;;) {
     __syncthreads();
@@ -114,6 +122,8 @@ __global__ void __launch_bounds__(kMaxThreads, 2) ransac_pairs_kernel(BatchArgs 
     int local_stats[4];
     __shared__ int s_stats[4];
     if (KIND == 0) {
+      dg::blk_prepare_tile32(c, tile32, &t32);
+      c.t32 = &t32;
       dg::FParams P;
       dg::f_thresholds(a.px_th, a.sym_check, &P.th, &P.sym_th);
       P.conf = a.conf; P.laf_coef = 0.0; P.max_iters = a.max_iters; P.metric = a.metric; P.degen = a.degen;
@@ -196,6 +206,11 @@ int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, doub
   size_t smem = sc_bytes + tile;
   a.pts_in_smem = cfg_smem_tile() ? 1 : 0;
   if (!a.pts_in_smem || smem > g_c.smem_optin) { smem = sc_bytes; a.pts_in_smem = 0; }
+  a.tile32_in_smem = 0;
+  if (KIND == 0 && 16 * (size_t)n <= 65536 && smem + dg::align_up(16 * (size_t)n, 128) <= g_c.smem_optin) {
+    a.tile32_in_smem = 1;
+    smem += dg::align_up(16 * (size_t)n, 128);
+  }
   const int kThreads = cfg_threads();
   auto kern = ransac_pairs_kernel<KIND>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

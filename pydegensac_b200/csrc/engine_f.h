@@ -27,8 +27,14 @@
 #include "ffit.h"
 #include "hfit.h"
 #include "degensac.h"
+#include "filter32.h"
 
 namespace dg {
+
+#ifdef DG_FILTER_CHECK
+static long g_filter_checked = 0, g_filter_violations = 0;
+static double g_filter_maxslack = 0.0;
+#endif
 
 // ------------------------------------------------------------------------------ LO hash table
 // The reference de-duplicates LO inlier sets with SuperFastHash + a 64-bucket chained table
@@ -258,19 +264,49 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
     bool keep = passall;
     if (!passall) {
       double f[9];
-      #pragma unroll 1
       for (int j = 0; j < 9; ++j) f[j] = W.cand[ci].f[j];
-      double J = 0.0;
+      if (c.t32) {
+        // FP32 upper bound of the MSAC score (filter32.h): a superset of the models that matter survives
+        FFilter32 ff;
+        f_filter_setup(P.metric, f, *c.t32, w94, &ff);
+        float J = 0.0f;
+        const Pt32* pts = c.t32->pts;
 #if DG_DEVICE_PASS
-      for (int i = c.lane; i < c.N; i += 32) {
+        for (int i = c.lane; i < c.N; i += 32) {
 #else
-      for (int i = 0; i < c.N; ++i) {
+        for (int i = 0; i < c.N; ++i) {
 #endif
-        const double e = f_resid(P.metric, f, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
-        if (e < w94) J += 1 - (e / w94);
+          J += f_filter_gain(ff, pts[i]);
+        }
+#if DG_DEVICE_PASS
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) J += __shfl_xor_sync(0xffffffffu, J, o);
+#endif
+        const double Jup = (double)J * (1.0 + 1.52587890625e-05) + 1e-3;
+#ifdef DG_FILTER_CHECK
+        {
+          double J64 = 0.0;
+          for (int i = 0; i < c.N; ++i) {
+            const double e = f_resid(P.metric, f, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+            if (e < w94) J64 += 1 - (e / w94);
+          }
+          if (c.lane == 0) { ++g_filter_checked; if (!(Jup >= J64) && J64 == J64) ++g_filter_violations; if (Jup - J64 > g_filter_maxslack) g_filter_maxslack = Jup - J64; }
+        }
+#endif
+        keep = Jup > T - 1e-9 * (1.0 + fabs(T));
+      } else {
+        double J = 0.0;
+#if DG_DEVICE_PASS
+        for (int i = c.lane; i < c.N; i += 32) {
+#else
+        for (int i = 0; i < c.N; ++i) {
+#endif
+          const double e = f_resid(P.metric, f, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+          if (e < w94) J += 1 - (e / w94);
+        }
+        J = warp_sum(J);
+        keep = J > T - 1e-9 * (1.0 + fabs(T));
       }
-      J = warp_sum(J);
-      keep = J > T - 1e-9 * (1.0 + fabs(T));
     }
     if (c.lane == 0 && keep) {
       const int slot = atomic_inc_shared(&c.sc->counter[1]);

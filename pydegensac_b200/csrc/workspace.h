@@ -21,6 +21,7 @@ DG_HD size_t workspace_bytes(int N, int chunk) {
   b += align_up(sizeof(int) * (size_t)(3 * chunk), 128);          // survivors
   b += align_up(sizeof(uint32_t) * kHashCap, 128) * 3;            // hash table
   b += align_up(sizeof(double) * (size_t)N, 128) * 4;             // SoA correspondences when not in smem
+  b += align_up(16 * (size_t)N, 128);                             // FP32 filter tile when not in smem
   return b;
 }
 
@@ -50,6 +51,9 @@ DG_HD void workspace_carve(unsigned char* base, int N, int chunk, Workspace* W, 
   W->hid = (int*)p; p += align_up(sizeof(uint32_t) * kHashCap, 128);
   W->hcap = kHashCap;
   *pts_soa = (double*)p;
+}
+DG_HD unsigned char* workspace_tile32(unsigned char* base, int N, int chunk) {
+  return base + workspace_bytes(N, chunk) - align_up(16 * (size_t)N, 128);
 }
 
 // Threshold conventions of the reference's binding layer (bindings.cpp:64-107, 297-318).

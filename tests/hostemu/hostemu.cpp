@@ -3,13 +3,22 @@
 // reference on a machine without a GPU.  Never loaded by the pydegensac_b200 package.
 #include <stdlib.h>
 #include <string.h>
+#define DG_FILTER_CHECK 1
 #include "../../pydegensac_b200/csrc/engine_f.h"
 #include "../../pydegensac_b200/csrc/engine_h.h"
 #include "../../pydegensac_b200/csrc/workspace.h"
 
 using namespace dg;
 
+static int g_use_filter32 = 1;
+extern "C" void emu_set_filter32(int on) { g_use_filter32 = on; }
+extern "C" void emu_filter_stats(long* checked, long* violations, double* maxslack) {
+  *checked = g_filter_checked; *violations = g_filter_violations; *maxslack = g_filter_maxslack;
+}
+
 struct Emu {
+  Tile32 t32;
+  Pt32* tile;
   Ctx c;
   Workspace W;
   BlockScratch sc;
@@ -30,6 +39,8 @@ static void emu_setup(Emu& E, const double* x1y1, const double* x2y2, int n, int
   E.c.tid = 0; E.c.nt = 1; E.c.lane = 0; E.c.wid = 0; E.c.nw = 1; E.c.N = n;
   E.c.x1 = x1; E.c.y1 = y1; E.c.x2 = x2; E.c.y2 = y2;
   E.c.sc = &E.sc;
+  E.c.t32 = nullptr;
+  E.tile = (Pt32*)malloc(sizeof(Pt32) * (size_t)n);
 }
 
 extern "C" int emu_find_fundamental(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
@@ -43,8 +54,9 @@ extern "C" int emu_find_fundamental(const double* x1y1, const double* x2y2, int 
   f_thresholds(px_th, sym_check, &P.th, &P.sym_th);
   P.conf = conf; P.laf_coef = 0; P.max_iters = max_iters; P.metric = error_type; P.degen = degen;
   P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk;
+  if (g_use_filter32) { blk_prepare_tile32(E.c, E.tile, &E.t32); E.c.t32 = &E.t32; }
   ransac_F_pair(E.c, P, E.W, F, mask, stats);
-  free(E.slab);
+  free(E.slab); free(E.tile);
   return 0;
 }
 
@@ -60,7 +72,7 @@ extern "C" int emu_find_homography(const double* x1y1, const double* x2y2, int n
   P.conf = conf; P.laf_coef = 0; P.max_iters = max_iters; P.metric = error_type;
   P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk;
   ransac_H_pair(E.c, P, E.W, H, mask, stats);
-  free(E.slab);
+  free(E.slab); free(E.tile);
   return 0;
 }
 
