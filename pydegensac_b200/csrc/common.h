@@ -36,9 +36,11 @@
 extern __device__ unsigned long long g_dg_prof[32];
 #define DG_PROF_BEGIN(id) long long prof_t_##id = (threadIdx.x == 0) ? clock64() : 0
 #define DG_PROF_END(id) do { if (threadIdx.x == 0) atomicAdd(&g_dg_prof[id], (unsigned long long)(clock64() - prof_t_##id)); } while (0)
+#define DG_PROF_COUNT(id, n) do { if (threadIdx.x == 0) atomicAdd(&g_dg_prof[id], (unsigned long long)(n)); } while (0)
 #else
 #define DG_PROF_BEGIN(id) ((void)0)
 #define DG_PROF_END(id) ((void)0)
+#define DG_PROF_COUNT(id, n) ((void)0)
 #endif
 
 namespace dg {

@@ -132,15 +132,10 @@ DG_ENGN void warp_h_fit_small(WarpScratch* ws, const double* u7, const int* idx,
     ws->A[9 * jj + i] = s;
   }
   DG_WSYNC();
-  warp_jacobi_eig9(ws, lane, W);
-  DG_WSYNC();
+  warp_smallest_eigvec9(ws, lane, W);
   if (lane == 0) {
-    int m = 0;
     #pragma unroll 1
-    for (int i = 1; i < 9; ++i)
-      if (ws->A[i * 10] < ws->A[m * 10]) m = i;
-    #pragma unroll 1
-    for (int i = 0; i < 9; ++i) h[i] = ws->V[i * 9 + m];
+    for (int i = 0; i < 9; ++i) h[i] = ws->cs[i];
     denorm_H(h, A1, A2);
   }
   DG_WSYNC();

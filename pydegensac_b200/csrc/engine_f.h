@@ -196,6 +196,86 @@ DG_ENGN bool run_lo_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, 
   return new_max;
 }
 
+#if DG_DEVICE_PASS
+// ---------------------------------------------------------------------------------------------
+// Wave stage A1 (device): Gauss-Jordan of the 7x9 sample systems with TWO THREADS PER SAMPLE, the matrix held in
+// registers (thread h of a lane pair owns columns 5h..5h+4 as a[lc][row]; pivots, pivot row choice and the six
+// multipliers travel through warp shuffles).  Every entry sees exactly the operations of the reference's
+// `nullspace` in the same order (utools.c:97-167: partial pivoting from the diagonal, pivot row divided, all other
+// rows eliminated), so the two null vectors are bit-identical to the one-thread routine (nullspace9) that the
+// host emulation and the non-generic fallback use -- without its 1.3 KB of local memory per thread.
+// Output per iteration k: W.nsbuf[16*(k-kbeg) + ..] = {-col7[0..6], -col8[0..6], generic?1:0}.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ void wave_F_pairsolve(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int kend) {
+  const int h = c.lane & 1;
+  const int slot = c.lane >> 1;
+  const int per_pass = c.nw * 16;
+  const unsigned full = 0xffffffffu;
+#pragma unroll 1
+  for (int base = kbeg + c.wid * 16; base <= kend; base += per_pass) {
+    const int k = base + slot;
+    const bool live = k <= kend;
+    int sel[7];
+    minimal_sample<7>(P.seed, (uint32_t)(live ? k : kbeg), c.N, sel);
+    double a[5][7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const int p = sel[r];
+      const double x1 = c.x1[p], y1 = c.y1[p], x2 = c.x2[p], y2 = c.y2[p];
+      if (h == 0) { a[0][r] = x2 * x1; a[1][r] = x2 * y1; a[2][r] = x2; a[3][r] = y2 * x1; a[4][r] = y2 * y1; }
+      else        { a[0][r] = y2;      a[1][r] = x1;      a[2][r] = y1; a[3][r] = 1.0;     a[4][r] = 0.0; }
+    }
+    bool generic = true;
+#pragma unroll
+    for (int col = 0; col < 7; ++col) {
+      const int owner = (col < 5) ? 0 : 1;
+      const int lc = col - 5 * owner;
+      int best = col;
+      double mag = 0.0;
+      if (h == owner) {
+        mag = fabs(a[lc][col]);
+#pragma unroll
+        for (int r = col + 1; r < 7; ++r) {
+          const double t = fabs(a[lc][r]);
+          if (mag < t) { mag = t; best = r; }
+        }
+      }
+      const int src = (c.lane & ~1) | owner;
+      best = __shfl_sync(full, best, src);
+      mag = __shfl_sync(full, mag, src);
+      if (mag < 1e-12) generic = false;
+#pragma unroll
+      for (int r = col + 1; r < 7; ++r) {
+        if (best == r) {
+#pragma unroll
+          for (int q = 0; q < 5; ++q) { const double t = a[q][col]; a[q][col] = a[q][r]; a[q][r] = t; }
+        }
+      }
+      const double p = __shfl_sync(full, a[lc][col], src);
+      double m[7];
+#pragma unroll
+      for (int r = 0; r < 7; ++r) m[r] = (r == col) ? 0.0 : __shfl_sync(full, a[lc][r], src);
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int gc = 5 * h + q;
+        if (gc >= col && gc < 9) {
+          a[q][col] /= p;
+#pragma unroll
+          for (int r = 0; r < 7; ++r)
+            if (r != col) a[q][r] -= m[r] * a[q][col];
+        }
+      }
+    }
+    if (live && h == 1) {
+      double* o = W.nsbuf + (size_t)(k - kbeg) * 16;
+#pragma unroll
+      for (int r = 0; r < 7; ++r) { o[r] = -a[2][r]; o[7 + r] = -a[3][r]; }
+      o[14] = generic ? 1.0 : 0.0;
+    }
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // WAVE: hypothesise iterations kbeg..kend (1-based), queue oriented-valid models, score them one
 // warp per model, keep those with J > T (or all when passall).  Returns the number kept; W.pass holds
@@ -207,21 +287,45 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
   DG_SYNC();
   if (c.tid == 0) { c.sc->counter[0] = 0; c.sc->counter[1] = 0; c.sc->counter[2] = 0; }
   DG_SYNC();
-  // stage A: one thread per minimal sample
+  // stage A: minimal solvers.  Device: A1 = two threads per sample eliminate in registers (wave_F_pairsolve),
+  // A2 = one thread per sample takes the null-space basis through the cubic and the oriented test.
   DG_PROF_BEGIN(0);
+  DG_PROF_COUNT(9, 1);
+  DG_PROF_COUNT(12, kend - kbeg + 1);
+#if DG_DEVICE_PASS
+  DG_PROF_BEGIN(10);
+  wave_F_pairsolve(c, P, W, kbeg, kend);
+  DG_SYNC();
+  DG_PROF_END(10);
+#endif
   #pragma unroll 1
   for (int k = kbeg + c.tid; k <= kend; k += c.nt) {
     int sel[7];
     minimal_sample<7>(P.seed, (uint32_t)k, c.N, sel);
-    double M[81], sol[81];
-    #pragma unroll 1
-    for (int i = 0; i < 7; ++i) {
-      const int p = sel[i];
-      f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], M + 9 * i);
+    double sol[18];
+    int nullsize = 2;
+#if DG_DEVICE_PASS
+    const double* ns = W.nsbuf + (size_t)(k - kbeg) * 16;
+    const bool generic = ns[14] != 0.0;
+    if (generic) {
+      #pragma unroll 1
+      for (int i = 0; i < 7; ++i) { sol[i] = ns[i]; sol[9 + i] = ns[7 + i]; }
+      sol[7] = 1.0; sol[8] = 0.0; sol[16] = 0.0; sol[17] = 1.0;
+    } else
+#endif
+    {
+      double M[81], full[81];
+      #pragma unroll 1
+      for (int i = 0; i < 7; ++i) {
+        const int p = sel[i];
+        f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], M + 9 * i);
+      }
+      #pragma unroll 1
+      for (int i = 63; i < 81; ++i) M[i] = 0.0;
+      nullsize = nullspace9(M, full);
+      #pragma unroll 1
+      for (int i = 0; i < 18; ++i) sol[i] = full[i];
     }
-    #pragma unroll 1
-    for (int i = 63; i < 81; ++i) M[i] = 0.0;
-    const int nullsize = nullspace9(M, sol);
     if (nullsize != 2) continue;
     if (k == kIterSam) c.sc->counter[2] = 1;
     double* f1 = sol;
@@ -254,6 +358,7 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
   DG_SYNC();
   DG_PROF_END(0);
   DG_PROF_BEGIN(1);
+  DG_PROF_COUNT(13, c.sc->counter[0]);
   int ncand = c.sc->counter[0];
   if (ncand > W.cand_cap) ncand = W.cand_cap;
   *valid_itersam = (c.sc->counter[2] != 0);

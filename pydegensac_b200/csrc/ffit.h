@@ -26,6 +26,7 @@ struct Workspace {
   int* itmp[4];
   unsigned char* btmp[4];
   Cand* cand;
+  double* nsbuf;    // per-iteration null-space bases of the wave (16 doubles each)
   int* pass;
   int cand_cap;
   uint32_t* hhash;
@@ -125,7 +126,10 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
         }
         DG_WSYNC();
       }
-      if (len > 0) warp_left_null_9xk(ws, len, c.lane, W);
+      // len == 8 (every iterated LSQ of the LO): lane-parallel Gauss-Jordan; rank-deficient or shorter: Householder
+      bool have = false;
+      if (len == 8) have = warp_null_8x9(ws, c.lane, W);
+      if (!have && len > 0) warp_left_null_9xk(ws, len, c.lane, W);
       if (c.lane == 0) {
         double q[9];
         #pragma unroll 1
@@ -200,16 +204,11 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
         ws->A[9 * jj + i] = s;
       }
       DG_WSYNC();
-      warp_jacobi_eig9(ws, c.lane, W);
-      DG_WSYNC();
+      warp_smallest_eigvec9(ws, c.lane, W);
       if (c.lane == 0) {
-        int m = 0;
-        #pragma unroll 1
-        for (int i = 1; i < 9; ++i)
-          if (ws->A[i * 10] < ws->A[m * 10]) m = i;
         double q[9];
         #pragma unroll 1
-        for (int i = 0; i < 9; ++i) q[i] = ws->V[i * 9 + m];
+        for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
         enforce_rank2(q);
         denorm_F(q, A1, A2);
         #pragma unroll 1

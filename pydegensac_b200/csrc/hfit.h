@@ -88,16 +88,11 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
         ws->A[9 * jj + i] = s;
       }
       DG_WSYNC();
-      warp_jacobi_eig9(ws, c.lane, W);
-      DG_WSYNC();
+      warp_smallest_eigvec9(ws, c.lane, W);
       if (c.lane == 0) {
-        int m = 0;
-        #pragma unroll 1
-        for (int i = 1; i < 9; ++i)
-          if (ws->A[i * 10] < ws->A[m * 10]) m = i;
         double q[9];
         #pragma unroll 1
-        for (int i = 0; i < 9; ++i) q[i] = ws->V[i * 9 + m];
+        for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
         denorm_H(q, A1, A2);
         #pragma unroll 1
         for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];

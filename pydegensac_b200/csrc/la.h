@@ -135,44 +135,49 @@ DG_HDN void min_eigvec9(double* C, double* v) {
 // norms are the singular values.  Used for the rank-2 projection of F (reference singulF,
 // Ftools.c:330-347, LAPACK dgesvd_) and for the epipole in Hdetect (DegUtils.c:109, CCMATH svduv).
 // ---------------------------------------------------------------------------------------------
-DG_HDN void svd3_onesided(const double* A, double* G, double* V, double* sv) {
-  #pragma unroll 1
+#if DG_DEVICE_PASS
+#define DG_RSQRT(x) rsqrt(x)
+#else
+#define DG_RSQRT(x) (1.0 / sqrt(x))
+#endif
+// One Hestenes rotation of columns (p,q) with compile-time indices: everything stays in registers.
+#define DG_SVD3_ROT(p, q)                                                                         \
+  {                                                                                               \
+    const double al = G[p] * G[p] + G[3 + p] * G[3 + p] + G[6 + p] * G[6 + p];                    \
+    const double be = G[q] * G[q] + G[3 + q] * G[3 + q] + G[6 + q] * G[6 + q];                    \
+    const double ga = G[p] * G[q] + G[3 + p] * G[3 + q] + G[6 + p] * G[6 + q];                    \
+    if (ga != 0.0 && ga * ga > 1e-30 * (al * be)) {                                               \
+      rotated = true;                                                                             \
+      const double zeta = be - al;                                                                \
+      const double hh = sqrt(zeta * zeta + 4.0 * ga * ga);                                        \
+      const double t = (zeta >= 0.0 ? 2.0 * ga : -2.0 * ga) / (fabs(zeta) + hh);                  \
+      const double c = DG_RSQRT(1.0 + t * t), s = c * t;                                          \
+      double gp, gq;                                                                              \
+      gp = G[p]; gq = G[q]; G[p] = c * gp - s * gq; G[q] = s * gp + c * gq;                        \
+      gp = G[3 + p]; gq = G[3 + q]; G[3 + p] = c * gp - s * gq; G[3 + q] = s * gp + c * gq;        \
+      gp = G[6 + p]; gq = G[6 + q]; G[6 + p] = c * gp - s * gq; G[6 + q] = s * gp + c * gq;        \
+      gp = V[p]; gq = V[q]; V[p] = c * gp - s * gq; V[q] = s * gp + c * gq;                        \
+      gp = V[3 + p]; gq = V[3 + q]; V[3 + p] = c * gp - s * gq; V[3 + q] = s * gp + c * gq;        \
+      gp = V[6 + p]; gq = V[6 + q]; V[6 + p] = c * gp - s * gq; V[6 + q] = s * gp + c * gq;        \
+    }                                                                                             \
+  }
+DG_HDN void svd3_onesided(const double* A, double* Gout, double* Vout, double* sv) {
+  double G[9], V[9];
+#pragma unroll
   for (int i = 0; i < 9; ++i) { G[i] = A[i]; V[i] = 0.0; }
   V[0] = V[4] = V[8] = 1.0;
-  #pragma unroll 1
-  for (int sweep = 0; sweep < 60; ++sweep) {
+#pragma unroll 1
+  for (int sweep = 0; sweep < 40; ++sweep) {
     bool rotated = false;
-    #pragma unroll 1
-    for (int p = 0; p < 2; ++p) {
-      #pragma unroll 1
-      for (int q = p + 1; q < 3; ++q) {
-        double al = 0.0, be = 0.0, ga = 0.0;
-        #pragma unroll 1
-        for (int i = 0; i < 3; ++i) {
-          al += G[3 * i + p] * G[3 * i + p];
-          be += G[3 * i + q] * G[3 * i + q];
-          ga += G[3 * i + p] * G[3 * i + q];
-        }
-        if (ga == 0.0 || fabs(ga) <= 1e-15 * sqrt(al * be)) continue;  // orthogonal to rounding level
-        rotated = true;
-        const double zeta = (be - al) / (2.0 * ga);
-        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-        #pragma unroll 1
-        for (int i = 0; i < 3; ++i) {
-          const double gp = G[3 * i + p], gq = G[3 * i + q];
-          G[3 * i + p] = c * gp - s * gq;
-          G[3 * i + q] = s * gp + c * gq;
-          const double vp = V[3 * i + p], vq = V[3 * i + q];
-          V[3 * i + p] = c * vp - s * vq;
-          V[3 * i + q] = s * vp + c * vq;
-        }
-      }
-    }
+    DG_SVD3_ROT(0, 1)
+    DG_SVD3_ROT(0, 2)
+    DG_SVD3_ROT(1, 2)
     if (!rotated) break;
   }
-  #pragma unroll 1
+#pragma unroll
   for (int c = 0; c < 3; ++c) sv[c] = sqrt(G[c] * G[c] + G[3 + c] * G[3 + c] + G[6 + c] * G[6 + c]);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { Gout[i] = G[i]; Vout[i] = V[i]; }
 }
 
 // Rank-2 projection F <- U diag(s0,s1,0) V^T == F - (F v_min) v_min^T   (reference: singulF)

@@ -44,25 +44,22 @@ DG_HD void minimal_sample(uint64_t seed, uint32_t k, int N, int* sel) {
   uint32_t r[8];
   philox4x32_10(0u, k, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
   if (M > 4) philox4x32_10(1u, k, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r + 4);
+  // Virtual pool: slots touched by earlier swaps are logged as (position, value) pairs, two per draw at FIXED
+  // log indices (2i, 2i+1), later entries overriding earlier ones -- every index below is a compile-time
+  // constant after unrolling, so the log lives in registers.
   int tp[2 * M], tv[2 * M];
-  int nt = 0;
 #pragma unroll
   for (int i = 0; i < M; ++i) {
     const int s = (int)((r[i] >> 1) % (uint32_t)(N - i));
     const int top = N - i - 1;
     int vs = s, vt = top;
-    for (int t = 0; t < nt; ++t) {
+#pragma unroll
+    for (int t = 0; t < 2 * i; ++t) {
       if (tp[t] == s) vs = tv[t];
       if (tp[t] == top) vt = tv[t];
     }
-    int t = 0;
-    while (t < nt && tp[t] != s) ++t;
-    if (t == nt) { tp[nt] = s; ++nt; }
-    tv[t] = vt;
-    t = 0;
-    while (t < nt && tp[t] != top) ++t;
-    if (t == nt) { tp[nt] = top; ++nt; }
-    tv[t] = vs;
+    tp[2 * i] = s;       tv[2 * i] = vt;        // pool[s]   <- value that sat at the top slot
+    tp[2 * i + 1] = top; tv[2 * i + 1] = vs;    // pool[top] <- the drawn value
     sel[i] = vs;
   }
 }

@@ -132,10 +132,152 @@ DG_ENGN void warp_jacobi_eig9(WarpScratch* ws, int lane, int W) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Eigenvector of the SMALLEST eigenvalue of the symmetric positive semi-definite 9x9 matrix in ws->A, written
+// to ws->cs[0..8] (visible to the whole warp on return).  This is all the LSQ fits need (the reference takes
+// column `argmin D` of LAPACK dsyev_, Ftools.c:376-389, Htools.c:126-127).
+//
+// Fast path: L D L^T factorisation (no pivoting: the matrix is a Gram matrix) followed by inverse iteration
+// x <- A^-1 x, which converges like (lambda_min / lambda_next)^k -- for an over-determined fit of noisy
+// correspondences that ratio is tiny, so 3-5 solves reach rounding level.  The result is accepted only if the
+// Rayleigh residual |A x - rho x| <= 1e-14 |A|_F; otherwise (clustered small eigenvalues, breakdown, NaN) the
+// parallel-order Jacobi above is used.  Dependent long-latency operations: ~9 divisions + a few solves,
+// instead of ~190 (sqrt, div, rsqrt) x 3 for seven Jacobi sweeps.
+// ---------------------------------------------------------------------------------------------
+#ifdef DG_EIG_STATS
+static long g_eig_calls = 0, g_eig_fallbacks = 0, g_eig_iters = 0;
+#endif
+DG_ENGN void warp_smallest_eigvec9(WarpScratch* ws, int lane, int W) {
+#ifdef DG_EIG_STATS
+  ++g_eig_calls;
+#endif
+  const double* A = ws->A;
+  double* L = ws->aux;          // 81: factor (lower triangle), unit diagonal implied
+  double* d = ws->aux + 81;     // 9 pivots
+  double* x = ws->aux + 90;     // 9 iterate
+  double* y = ws->aux + 99;     // 9 work
+  double* red = ws->aux + 108;  // scalars
+  double fro = 0.0;
+#pragma unroll 1
+  for (int t = lane; t < 81; t += W) { const double v = A[t]; L[t] = v; fro += v * v; }
+  fro = wl_sum(fro);
+  DG_WSYNC();
+  bool ok = (fro > 0.0) && (fro == fro) && (fro < 1e300);
+  const double tiny = sqrt(fro) * 1e-30;
+  if (ok) {
+#pragma unroll 1
+    for (int k = 0; k < 9; ++k) {
+      double dk = L[k * 10];
+      if (!(dk > tiny)) dk = tiny;          // exactly singular / rounding-negative pivot: regularise
+      const double inv = 1.0 / dk;
+      if (lane == 0) d[k] = dk;
+      // trailing update of the lower triangle: L[i][j] -= L[i][k] * L[j][k] / dk   (k < j <= i)
+      const int m = 8 - k;                  // trailing size
+      const int ntask = m * (m + 1) / 2;
+#pragma unroll 1
+      for (int t = lane; t < ntask; t += W) {
+        int ii = 0;
+        while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
+        const int jj = t - ii * (ii + 1) / 2;
+        const int i = k + 1 + ii, j = k + 1 + jj;
+        L[i * 9 + j] -= (L[i * 9 + k] * inv) * L[j * 9 + k];
+      }
+      DG_WSYNC();
+#pragma unroll 1
+      for (int i = k + 1 + lane; i < 9; i += W) L[i * 9 + k] *= inv;
+      DG_WSYNC();
+    }
+#pragma unroll 1
+    for (int i = lane; i < 9; i += W) x[i] = 1.0 / 3.0;
+    DG_WSYNC();
+    double prev_change = 1.0;
+#pragma unroll 1
+    for (int it = 0; it < 12; ++it) {
+#ifdef DG_EIG_STATS
+      ++g_eig_iters;
+#endif
+#pragma unroll 1
+      for (int i = lane; i < 9; i += W) y[i] = x[i];
+      DG_WSYNC();
+#pragma unroll 1
+      for (int k = 0; k < 8; ++k) {          // forward substitution with the unit lower factor
+#pragma unroll 1
+        for (int i = k + 1 + lane; i < 9; i += W) y[i] -= L[i * 9 + k] * y[k];
+        DG_WSYNC();
+      }
+#pragma unroll 1
+      for (int i = lane; i < 9; i += W) y[i] /= d[i];
+      DG_WSYNC();
+#pragma unroll 1
+      for (int k = 8; k > 0; --k) {          // backward substitution with the transposed factor
+#pragma unroll 1
+        for (int i = lane; i < k; i += W) y[i] -= L[k * 9 + i] * y[k];
+        DG_WSYNC();
+      }
+      double n2 = 0.0, dot = 0.0;
+#pragma unroll 1
+      for (int i = lane; i < 9; i += W) { n2 += y[i] * y[i]; dot += y[i] * x[i]; }
+      n2 = wl_sum(n2);
+      dot = wl_sum(dot);
+      if (!(n2 > 0.0) || !(n2 < 1e300)) { ok = false; break; }
+      const double sc = (dot < 0.0 ? -1.0 : 1.0) / sqrt(n2);
+      double ch = 0.0;
+#pragma unroll 1
+      for (int i = lane; i < 9; i += W) {
+        const double xn = y[i] * sc;
+        const double df = xn - x[i];
+        ch += df * df;
+        x[i] = xn;
+      }
+      ch = wl_sum(ch);
+      DG_WSYNC();
+      if (ch < 1e-31) break;                 // iterate unchanged to rounding level
+      if (it >= 6 && ch > 0.25 * prev_change) { ok = false; break; }   // slow: clustered eigenvalues -> Jacobi
+      prev_change = ch;
+    }
+  }
+  if (ok) {   // Rayleigh residual against the ORIGINAL matrix
+    double rho = 0.0;
+#pragma unroll 1
+    for (int i = lane; i < 9; i += W) {
+      double s = 0.0;
+      for (int j = 0; j < 9; ++j) s += A[i * 9 + j] * x[j];
+      y[i] = s;
+      rho += s * x[i];
+    }
+    rho = wl_sum(rho);
+    DG_WSYNC();
+    double r2 = 0.0;
+#pragma unroll 1
+    for (int i = lane; i < 9; i += W) { const double r = y[i] - rho * x[i]; r2 += r * r; }
+    r2 = wl_sum(r2);
+    ok = (r2 <= 1e-28 * fro);
+  }
+  DG_WSYNC();
+  if (ok) {
+#pragma unroll 1
+    for (int i = lane; i < 9; i += W) ws->cs[i] = x[i];
+    DG_WSYNC();
+    return;
+  }
+#ifdef DG_EIG_STATS
+  ++g_eig_fallbacks;
+#endif
+  warp_jacobi_eig9(ws, lane, W);
+  DG_WSYNC();
+  if (lane == 0) {
+    int m = 0;
+    for (int i = 1; i < 9; ++i)
+      if (ws->A[i * 10] < ws->A[m * 10]) m = i;
+    for (int i = 0; i < 9; ++i) ws->cs[i] = ws->V[i * 9 + m];
+  }
+  DG_WSYNC();
+}
+
 // Eigenvector of the smallest eigenvalue of the symmetric matrix whose lower triangle (row-major packed,
 // 45 entries: (0,0),(1,0),(1,1),(2,0)...) is in `packed`; result in ws->cs[0..8] (visible after DG_WSYNC).
 DG_ENGN void warp_min_eigvec9_packed(WarpScratch* ws, const double* packed, int lane, int W) {
-  #pragma unroll 1
+#pragma unroll 1
   for (int t = lane; t < 45; t += W) {
     int i = 0;
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
@@ -145,17 +287,76 @@ DG_ENGN void warp_min_eigvec9_packed(WarpScratch* ws, const double* packed, int 
     ws->A[9 * j + i] = v;
   }
   DG_WSYNC();
-  warp_jacobi_eig9(ws, lane, W);
-  DG_WSYNC();
-  if (lane == 0) {
-    int m = 0;
-    #pragma unroll 1
-    for (int i = 1; i < 9; ++i)
-      if (ws->A[i * 10] < ws->A[m * 10]) m = i;
-    #pragma unroll 1
-    for (int i = 0; i < 9; ++i) ws->cs[i] = ws->V[i * 9 + m];
+  warp_smallest_eigvec9(ws, lane, W);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Unit null vector of the 8 x 9 system whose rows are the 8 columns of the 9 x 8 row-major matrix Z in
+// ws->A[0..72) (i.e. the vector orthogonal to all eight correspondences' coefficient columns), by Gauss-Jordan
+// elimination with partial pivoting spread over the lanes (every lane owns 2-3 matrix entries; per pivot:
+// search, one division per lane, one fused update).  ~8 dependent divisions instead of the ~16 sqrt/div plus
+// long dot-product chains of the Householder route below.  Returns false (all lanes) when a pivot vanishes
+// (rank-deficient sample): the caller then uses the Householder route.  Result in ws->cs[0..8].
+// ---------------------------------------------------------------------------------------------
+DG_ENGN bool warp_null_8x9(WarpScratch* ws, int lane, int W) {
+  double* M = ws->aux;          // 8 x 9 row-major working copy (row = correspondence)
+  double* mult = ws->aux + 80;  // multipliers of the current pivot column
+  int* piv = reinterpret_cast<int*>(ws->aux + 96);
+#pragma unroll 1
+  for (int t = lane; t < 72; t += W) {
+    const int r = t / 9, cc = t % 9;
+    M[t] = ws->A[cc * 8 + r];
   }
   DG_WSYNC();
+  bool ok = true;
+#pragma unroll 1
+  for (int col = 0; col < 8; ++col) {
+    if (lane == 0) {
+      int best = col;
+      double mag = fabs(M[col * 9 + col]);
+#pragma unroll
+      for (int r = 1; r < 8; ++r) {
+        const int rr = col + r;
+        if (rr < 8) {
+          const double v = fabs(M[rr * 9 + col]);
+          if (v > mag) { mag = v; best = rr; }
+        }
+      }
+      piv[0] = (mag > 0.0 && mag == mag) ? best : -1;
+    }
+    DG_WSYNC();
+    const int best = piv[0];
+    if (best < 0) { ok = false; break; }
+    // swap rows col <-> best, scale the pivot row, publish the multipliers
+    const double p = M[best * 9 + col];
+#pragma unroll 1
+    for (int cc = lane; cc < 9; cc += W) {
+      const double a = M[col * 9 + cc], b = M[best * 9 + cc];
+      M[best * 9 + cc] = a;
+      M[col * 9 + cc] = b / p;
+    }
+    DG_WSYNC();
+#pragma unroll 1
+    for (int r = lane; r < 8; r += W) mult[r] = M[r * 9 + col];
+    DG_WSYNC();
+#pragma unroll 1
+    for (int t = lane; t < 72; t += W) {
+      const int r = t / 9, cc = t % 9;
+      if (r != col && cc >= col) M[t] -= mult[r] * M[col * 9 + cc];
+    }
+    DG_WSYNC();
+  }
+  if (ok) {
+    double n2 = 1.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) n2 += M[r * 9 + 8] * M[r * 9 + 8];
+    const double sc = 1.0 / sqrt(n2);
+    DG_WSYNC();
+#pragma unroll 1
+    for (int i = lane; i < 9; i += W) ws->cs[i] = (i < 8) ? -M[i * 9 + 8] * sc : sc;
+  }
+  DG_WSYNC();
+  return ok;
 }
 
 // Unit vector orthogonal to the `len` (1..8) columns of the 9 x len row-major matrix in ws->A[0 .. 9*len)

@@ -19,6 +19,7 @@ DG_HD size_t workspace_bytes(int N, int chunk) {
   b += align_up((size_t)N, 128) * 4;                              // btmp[4]
   b += align_up(sizeof(Cand) * (size_t)(3 * chunk), 128);         // hypothesis queue
   b += align_up(sizeof(int) * (size_t)(3 * chunk), 128);          // survivors
+  b += align_up(sizeof(double) * 16 * (size_t)chunk, 128);        // null-space bases of the wave
   b += align_up(sizeof(uint32_t) * kHashCap, 128) * 3;            // hash table
   b += align_up(sizeof(double) * (size_t)N, 128) * 4;             // SoA correspondences when not in smem
   b += align_up(16 * (size_t)N, 128);                             // FP32 filter tile when not in smem
@@ -45,6 +46,7 @@ DG_HD void workspace_carve(unsigned char* base, int N, int chunk, Workspace* W, 
   for (int i = 0; i < 4; ++i) { W->btmp[i] = p; p += rowb; }
   W->cand = (Cand*)p; p += align_up(sizeof(Cand) * (size_t)(3 * chunk), 128);
   W->pass = (int*)p; p += align_up(sizeof(int) * (size_t)(3 * chunk), 128);
+  W->nsbuf = (double*)p; p += align_up(sizeof(double) * 16 * (size_t)chunk, 128);
   W->cand_cap = 3 * chunk;
   W->hhash = (uint32_t*)p; p += align_up(sizeof(uint32_t) * kHashCap, 128);
   W->hlen = (int*)p; p += align_up(sizeof(uint32_t) * kHashCap, 128);

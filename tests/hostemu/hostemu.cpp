@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 #define DG_FILTER_CHECK 1
+#define DG_EIG_STATS 1
 #include "../../pydegensac_b200/csrc/engine_f.h"
 #include "../../pydegensac_b200/csrc/engine_h.h"
 #include "../../pydegensac_b200/csrc/workspace.h"
@@ -99,3 +100,5 @@ extern "C" int emu_checksample(const double* F, const double* u7, double th, dou
   return 0;
 }
 extern "C" void emu_gkr_v3(const double* A, double* v) { gkr_third_right_vector3(A, v); }
+
+extern "C" void emu_eig_stats(long* calls, long* fallbacks, long* iters) { *calls = g_eig_calls; *fallbacks = g_eig_fallbacks; *iters = g_eig_iters; }

@@ -22,3 +22,4 @@ print("pairs", P, "kernel ms %.1f" % ms, "-> %.0f pairs/s" % (P / ms * 1e3))
 tot = sum(buf[i] for i in (0, 1, 2))
 for i in range(9):
     print("%-28s %10.3f Mcycles/pair  %5.1f%%" % (names[i], buf[i] / P / 1e6, 100.0 * buf[i] / max(tot, 1)))
+print("waves/pair %.1f  iterations waved/pair %.0f  candidates/pair %.0f  A1 %.3f Mcycles/pair" % (buf[9] / P, buf[12] / P, buf[13] / P, buf[10] / P / 1e6))
