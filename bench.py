@@ -72,10 +72,27 @@ def cpu_reference_rate(pairs_per_proc, procs, seed0=100000):
 
 
 def host_cores():
+    """Cores this process may actually use: CPU affinity capped by the cgroup CPU quota (a container that sees
+    128 logical CPUs but has cpu.max = 16 CPUs gets 16 worker processes, not 128 oversubscribed ones)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
 
 
 def run_reference_arm(args):
@@ -307,8 +324,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=1024)
-    ap.add_argument("--cpu-pairs-per-core", type=int, default=4)
+    ap.add_argument("--pairs-per-gpu", type=int, default=4096)
+    ap.add_argument("--cpu-pairs-per-core", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

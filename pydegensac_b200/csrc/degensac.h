@@ -29,34 +29,26 @@ DG_HDN void h_from_F_3pts(const double* F, const double* u7, const int* tri, dou
   gkr_third_right_vector3(F, ec);  // column 2 of CCMATH's V (usually, not always, F ec = 0)
   const double Ex[9] = {0, -ec[2], ec[1], ec[2], 0, -ec[0], -ec[1], ec[0], 0};
   double A[9];  // A = [ec]x * F^T
-  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
-    #pragma unroll 1
     for (int j = 0; j < 3; ++j) {
       double s = 0.0;
-      #pragma unroll 1
       for (int k = 0; k < 3; ++k) s += Ex[3 * i + k] * F[3 * j + k];
       A[3 * i + j] = s;
     }
   double b[3], M[9];
-  #pragma unroll 1
   for (int t = 0; t < 3; ++t) {
     const double* p = u7 + 4 * tri[t];
     const double a1[3] = {p[0], p[1], 1.0};
     const double a2[3] = {p[2], p[3], 1.0};
     double Ab[3], p1[3], p2[3];
-    #pragma unroll 1
     for (int i = 0; i < 3; ++i) {
       double s = 0.0;
-      #pragma unroll 1
       for (int k = 0; k < 3; ++k) s += A[3 * i + k] * a2[k];
       Ab[i] = s;
     }
     cross3(p1, a1, Ab);
-    #pragma unroll 1
     for (int i = 0; i < 3; ++i) {
       double s = 0.0;
-      #pragma unroll 1
       for (int k = 0; k < 3; ++k) s += (-Ex[3 * i + k]) * a1[k];
       p2[i] = s;
     }
@@ -65,14 +57,10 @@ DG_HDN void h_from_F_3pts(const double* F, const double* u7, const int* tri, dou
   }
   const int sing = inv3(M);
   double v[3];
-  #pragma unroll 1
   for (int i = 0; i < 3; ++i) v[i] = M[3 * i] * b[0] + M[3 * i + 1] * b[1] + M[3 * i + 2] * b[2];
-  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
-    #pragma unroll 1
     for (int j = 0; j < 3; ++j) H[i + 3 * j] = A[3 * i + j] - ec[i] * v[j];
   if (isnan(H[0]) || isinf(H[0]) || sing) {
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i) H[i] = 0.0;
     H[0] = H[4] = H[8] = 1.0;
   }
@@ -90,7 +78,6 @@ DG_ENGN void warp_h_fit_small(WarpScratch* ws, const double* u7, const int* idx,
       const double* p = u7 + 4 * idx[j];
       A1[1] += p[0]; A1[2] += p[1]; A2[1] += p[2]; A2[2] += p[3];
     }
-    #pragma unroll 1
     for (int i = 1; i < 3; ++i) { A1[i] /= len; A2[i] /= len; }
     #pragma unroll 1
     for (int j = 0; j < len; ++j) {
@@ -112,7 +99,6 @@ DG_ENGN void warp_h_fit_small(WarpScratch* ws, const double* u7, const int* idx,
       b[0] = p[2] * A2[0] + A2[1]; b[1] = p[3] * A2[0] + A2[2]; b[2] = 1.0;
       double* r0 = rows + 18 * j;
       double* r1 = r0 + 9;
-      #pragma unroll 1
       for (int t = 0; t < 3; ++t) {
         r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
         r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
@@ -134,7 +120,6 @@ DG_ENGN void warp_h_fit_small(WarpScratch* ws, const double* u7, const int* idx,
   DG_WSYNC();
   warp_smallest_eigvec9(ws, lane, W);
   if (lane == 0) {
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i) h[i] = ws->cs[i];
     denorm_H(h, A1, A2);
   }
@@ -152,7 +137,6 @@ DG_ENGN bool warp_checksample_triplet(WarpScratch* ws, const double* F, const do
 #ifdef DG_TRACE
     if (t == 0) {
       fprintf(stderr, "CSIN F=");
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) fprintf(stderr, "%.17g ", F[i]);
       fprintf(stderr, "u7=");
       #pragma unroll 1
@@ -162,12 +146,10 @@ DG_ENGN bool warp_checksample_triplet(WarpScratch* ws, const double* F, const do
     fprintf(stderr, "HDET t=%d H=%.10g %.10g %.10g %.10g\n", t, H[0], H[1], H[2], H[8]);
 #endif
     double Ds[7];
-    #pragma unroll 1
     for (int j = 0; j < 7; ++j) {
       Ds[j] = h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]);
       idx[j] = j;
     }
-    #pragma unroll 1
     for (int i = 0; i < 7; ++i)      // exchange sort of the reference's sortDs (DegUtils.c:164-183)
       #pragma unroll 1
       for (int j = i + 1; j < 7; ++j)
@@ -180,13 +162,11 @@ DG_ENGN bool warp_checksample_triplet(WarpScratch* ws, const double* F, const do
   warp_h_fit_small(ws, u7, idx, 5, H, lane, W);
   int cnt = 0;
   if (lane == 0)
-    #pragma unroll 1
     for (int j = 0; j < 7; ++j)
       if (h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]) < th) ++cnt;
 #ifdef DG_TRACE
   if (lane == 0) {
     double Ds[7];
-    #pragma unroll 1
     for (int j = 0; j < 7; ++j) Ds[j] = h_resid_sampson(H, u7[4 * j], u7[4 * j + 1], u7[4 * j + 2], u7[4 * j + 3]);
     fprintf(stderr, "CS trip=%d cnt=%d Ds=%.6g %.6g %.6g %.6g %.6g %.6g %.6g H=%.10g %.10g %.10g\n", t, cnt, Ds[0], Ds[1], Ds[2], Ds[3], Ds[4], Ds[5], Ds[6], H[0] / H[8], H[1] / H[8], H[2] / H[8]);
   }
@@ -214,12 +194,10 @@ DG_ENGN bool blk_checksample(const Ctx& c, const double* F, const double* u7, do
   }
   DG_SYNC();
   int win = -1;
-  #pragma unroll 1
   for (int t = 0; t < 5; ++t)
     if (c.sc->bci[t]) { win = t; break; }
   // the reference leaves the LAST tested triplet's H in the buffer when none succeeds; it is unused then
   const int src = win < 0 ? 4 : win;
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) H[i] = (src < 3) ? c.sc->bc[9 * src + i] : c.sc->vec[9 * (src - 3) + i];
   DG_SYNC();
   return win >= 0;
@@ -238,7 +216,6 @@ DG_ENGN Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** rows, in
   Score S = make_score(), Ss, maxS;
   maxS = blk_inlidxs(c, rows[e[4]], th, inl);
   if (maxS.I < 4) return S;
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) h[i] = Hio[i];
   if (maxS.I <= inlLimit) {
     blk_fit_H(c, inl, (int)maxS.I, h);
@@ -256,7 +233,6 @@ DG_ENGN Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** rows, in
       e[1] = e[0];
       e[0] = d;
       d = e[1];
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) Hio[i] = h[i];
     }
     if (Ss.I < 4) return maxS;
@@ -274,7 +250,6 @@ DG_ENGN Score plane_iter_H(const Ctx& c, Workspace& W, int* e, double** rows, in
     maxS = S;
     e[1] = e[0];
     e[0] = d;
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i) Hio[i] = h[i];
   }
   return maxS;
@@ -298,7 +273,6 @@ DG_ENGN unsigned blk_inner_H(const Ctx& c, Workspace& W, double* H, double th, u
     if (ssiz > 12) ssiz = 12;
     int t = e[2]; e[2] = e[0]; e[0] = t;
     double h[9];
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i) h[i] = H[i];
     #pragma unroll 1
     for (int rep = 0; rep < kRanRep; ++rep) {
@@ -310,7 +284,6 @@ DG_ENGN unsigned blk_inner_H(const Ctx& c, Workspace& W, double* H, double th, u
       if (score_less(maxS, S)) {
         maxS = S;
         t = e[2]; e[2] = e[0]; e[0] = t;
-        #pragma unroll 1
         for (int i = 0; i < 9; ++i) H[i] = h[i];
       }
     }
@@ -399,7 +372,6 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
   double* Ds = W.dtmp[5];
   int* usam = W.itmp[2];  // 10 indices
   unsigned max_i = 0, max_s = 0;
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) F[i] = 1.0;
   #pragma unroll 1
   for (int i = c.tid; i < c.N; i += c.nt) inl[i] = 0;
@@ -411,7 +383,6 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
     if (c.tid == 0) {
       DrawCursor t = cur;
       int tp[12], tv[12], nt;
-      #pragma unroll 1
       for (int side = 0; side < 2; ++side) {
         const int len = side ? nO : nH, s = side ? 4 : 6;
         const int* src = side ? uO : uH;
@@ -457,7 +428,6 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
     if (max_i < no_i) {
       #pragma unroll 1
       for (int i = c.tid; i < c.N; i += c.nt) inl[i] = v[i];
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) F[i] = aF[i];
       max_i = no_i;
       DG_SYNC();
@@ -468,7 +438,6 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
       if (max_i < no_i) {
         #pragma unroll 1
         for (int i = c.tid; i < c.N; i += c.nt) inl[i] = v[i];
-        #pragma unroll 1
         for (int i = 0; i < 9; ++i) F[i] = aF[i];
         max_i = no_i;
         DG_SYNC();
@@ -495,12 +464,9 @@ DG_HD void f_from_plane_parallax(const double* H, double ax1, double ay1, double
   ec[0] = ec[0] / n; ec[1] = ec[1] / n; ec[2] = ec[2] / n;
   const double S[9] = {0, -ec[2], ec[1], ec[2], 0, -ec[0], -ec[1], ec[0], 0};
   // Ht (row-major transpose of the column-major array, i.e. Ht[i][j] = H[j*3+i]); G = S * Ht ; F = G^T
-  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
-    #pragma unroll 1
     for (int j = 0; j < 3; ++j) {
       double s = 0.0;
-      #pragma unroll 1
       for (int k = 0; k < 3; ++k) s += S[3 * i + k] * H[j * 3 + k];
       F[3 * j + i] = s;
     }
@@ -545,7 +511,6 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
       DrawCursor t = cur;
       #pragma unroll 1
       for (int s = 0; s < nw; ++s) {
-        #pragma unroll 1
         for (int pos = 0; pos < 2; ++pos) {
           const int idx = pos + 1 + (int)(next_draw(t) % (uint32_t)(nN - pos - 1));
           const int a = ptr[pos]; ptr[pos] = ptr[idx]; ptr[idx] = a;
@@ -591,7 +556,6 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
       int idxs[2 * 128];
       #pragma unroll 1
       for (int s = ev + 1; s < nw; ++s)
-        #pragma unroll 1
         for (int pos = 0; pos < 2; ++pos) idxs[2 * s + pos] = pos + 1 + (int)(next_draw(t) % (uint32_t)(nN - pos - 1));
       #pragma unroll 1
       for (int s = nw - 1; s > ev; --s)
@@ -629,7 +593,6 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
       const unsigned both = (unsigned)blk_sum_i(c, cnt2);
       if (ninl > max_i) {
         max_i = ninl;
-        #pragma unroll 1
         for (int i = 0; i < 9; ++i) F[i] = Fnew[i];
         maxni = both;
         const unsigned ns = (unsigned)nsamples((int)maxni, nN, 2, 0.999);

@@ -30,14 +30,15 @@ namespace {
 constexpr int kMaxThreads = 256;
 constexpr int kChunk = 512;
 
-// CTA shape.  The replay phase is a latency chain (LO, DEGENSAC), so throughput comes from keeping MANY pairs in
-// flight per SM: small CTAs (default 64 threads) with the FP64 correspondences in the per-CTA global slab
-// (L1/L2 resident) instead of a 64 KB shared-memory tile.  DGB200_THREADS / DGB200_SMEM_TILE override for experiments.
+// CTA shape.  256 threads x 2 CTAs per SM measured fastest on B200 (profiles/README.md): the waves and the O(N)
+// passes of the replay want the 8 warps, while more, smaller CTAs per SM lose to instruction-cache misses (each
+// CTA walks a different part of a ~300 KB code image).  FP64 correspondences live in the per-CTA global slab
+// (L1/L2 resident), the FP32 filter tile in shared memory.  DGB200_THREADS / DGB200_SMEM_TILE override for experiments.
 int cfg_threads() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DGB200_THREADS");
-    v = e ? atoi(e) : 64;
+    v = e ? atoi(e) : 256;
     if (v < 32) v = 32;
     if (v > kMaxThreads) v = kMaxThreads;
     v = (v / 32) * 32;

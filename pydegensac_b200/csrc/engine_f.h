@@ -95,7 +95,6 @@ DG_ENGN Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int* e, in
       e[1] = e[0];
       e[0] = d;
       d = e[1];
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) Fio[i] = f[i];
     }
     Ss = blk_inlidxs(c, W.err[d], ths * kMWM, inl);
@@ -114,7 +113,6 @@ DG_ENGN Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int* e, in
     maxS = S;
     e[1] = e[0];
     e[0] = d;
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i) Fio[i] = f[i];
   }
   return maxS;
@@ -140,7 +138,6 @@ DG_ENGN Score lo_inner_F(const Ctx& c, const FParams& P, Workspace& W, int* e, i
     if (score_less(maxS, S)) {
       maxS = S;
       t = e[2]; e[2] = e[0]; e[0] = t;
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) Fout[i] = f[i];
       #pragma unroll 1
       for (int j = c.tid; j < (int)maxS.I; j += c.nt) W.intbuff_best[j] = W.intbuff[j];
@@ -187,7 +184,6 @@ DG_ENGN bool run_lo_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, 
     if (do_update) {
       const int t = st.e[0]; st.e[0] = st.e[3]; st.e[3] = t;
       st.maxS = S;
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) st.F[i] = f[i];
       new_max = true;
     }
@@ -308,14 +304,12 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
     const double* ns = W.nsbuf + (size_t)(k - kbeg) * 16;
     const bool generic = ns[14] != 0.0;
     if (generic) {
-      #pragma unroll 1
       for (int i = 0; i < 7; ++i) { sol[i] = ns[i]; sol[9 + i] = ns[7 + i]; }
       sol[7] = 1.0; sol[8] = 0.0; sol[16] = 0.0; sol[17] = 1.0;
     } else
 #endif
     {
       double M[81], full[81];
-      #pragma unroll 1
       for (int i = 0; i < 7; ++i) {
         const int p = sel[i];
         f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], M + 9 * i);
@@ -334,7 +328,6 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
     seven_pt_cubic(f1, f2, poly);
     const int nsol = cubic_real_roots(poly, roots);
     double sx1[7], sy1[7], sx2[7], sy2[7];
-    #pragma unroll 1
     for (int t = 0; t < 7; ++t) {  // reference samidx order = reverse draw order
       const int p = sel[6 - t];
       sx1[t] = c.x1[p]; sy1[t] = c.y1[p]; sx2[t] = c.x2[p]; sy2[t] = c.y2[p];
@@ -342,13 +335,11 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
     #pragma unroll 1
     for (int i = 0; i < nsol; ++i) {
       double f[9];
-      #pragma unroll 1
       for (int j = 0; j < 9; ++j) f[j] = f1[j] * roots[i] + f2[j] * (1 - roots[i]);
       if (!oriented_ok_F(f, sx1, sy1, sx2, sy2, 7)) continue;
       const int slot = atomic_inc_shared(&c.sc->counter[0]);
       if (slot < W.cand_cap) {
         Cand& cd = W.cand[slot];
-        #pragma unroll 1
         for (int j = 0; j < 9; ++j) cd.f[j] = f[j];
         cd.k = k;
         cd.root = i;
@@ -470,7 +461,6 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
   DG_PROF_BEGIN(2);
   int sel[7], samidx[7];
   minimal_sample<7>(P.seed, (uint32_t)k, c.N, sel);
-  #pragma unroll 1
   for (int t = 0; t < 7; ++t) samidx[t] = sel[6 - t];
   st.cur.seed = P.seed; st.cur.k = (uint32_t)k; st.cur.j = 8;
   #pragma unroll 1
@@ -478,7 +468,6 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
     const Cand& cd = W.cand[W.pass[pos + q]];
     const int i = cd.root;
     double f[9];
-    #pragma unroll 1
     for (int j = 0; j < 9; ++j) f[j] = cd.f[j];
     int d = st.e[i];
     blk_resid_F(c, P.metric, f, W.err[d]);
@@ -493,7 +482,6 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
       st.e[i] = st.e[3];
       st.e[3] = d;
       st.maxS = S;
-      #pragma unroll 1
       for (int j = 0; j < 9; ++j) st.F[j] = f[j];
       new_max = true;
     }
@@ -506,7 +494,6 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
       double H[9];
       if (P.degen) {
         double u7[28];
-        #pragma unroll 1
         for (int t = 0; t < 7; ++t) {
           const int p = samidx[t];
           u7[4 * t] = c.x1[p]; u7[4 * t + 1] = c.y1[p]; u7[4 * t + 2] = c.x2[p]; u7[4 * t + 3] = c.y2[p];
@@ -527,7 +514,6 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
           if (I > st.maxS.I) {
             blk_resid_F(c, P.metric, f, W.err[st.e[3]]);
             st.maxS.I = I;
-            #pragma unroll 1
             for (int j = 0; j < 9; ++j) st.F[j] = f[j];
             new_max = true;
             d = st.e[3];
@@ -548,12 +534,10 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
         do_iterate = (k > kIterSam);
         st.e[4] = d;
         ++st.non_degen;
-        #pragma unroll 1
         for (int t = 0; t < 7; ++t) st.samidxBest[t] = samidx[t];
         #pragma unroll 1
         for (int j = c.tid; j < c.N; j += c.nt) W.errBest[j] = W.err[d][j];
         DG_SYNC();
-        #pragma unroll 1
         for (int j = 0; j < 9; ++j) st.FBest[j] = f[j];
       }
     }
@@ -578,18 +562,14 @@ DG_ENGN void ransac_F_pair(const Ctx& c, const FParams& P, Workspace& W, double*
   FState st;
   st.maxS = make_score(); st.maxSs = make_score();
   st.maxS.I = 8; st.maxSs.I = 8;
-  #pragma unroll 1
   for (int i = 0; i < 4; ++i) st.e[i] = i;
   st.e[4] = 3;
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) { st.F[i] = 0.0; st.FBest[i] = 0.0; }
-  #pragma unroll 1
   for (int i = 0; i < 7; ++i) st.samidxBest[i] = 0;
   st.max_sam = P.max_iters; st.iter_cnt = 0; st.degen_cnt = 0; st.non_degen = 0; st.iterID = 0; st.Ihmax = 0;
   st.ht.n = 0;
   st.cur.seed = P.seed; st.cur.k = 0; st.cur.j = 1;
   // residual rows start zeroed (the reference reads uninitialised malloc memory if no model is ever scored)
-  #pragma unroll 1
   for (int r = 0; r < 4; ++r)
     #pragma unroll 1
     for (int j = c.tid; j < c.N; j += c.nt) W.err[r][j] = 0.0;
@@ -639,7 +619,6 @@ DG_ENGN void ransac_F_pair(const Ctx& c, const FParams& P, Workspace& W, double*
     double H[9], f[9];
     if (P.degen) {
       double u7[28];
-      #pragma unroll 1
       for (int t = 0; t < 7; ++t) {
         const int p = st.samidxBest[t];
         u7[4 * t] = c.x1[p]; u7[4 * t + 1] = c.y1[p]; u7[4 * t + 2] = c.x2[p]; u7[4 * t + 3] = c.y2[p];
@@ -654,14 +633,12 @@ DG_ENGN void ransac_F_pair(const Ctx& c, const FParams& P, Workspace& W, double*
       if ((int)I > st.Ihmax) st.Ihmax = (int)I;
       if (I > 6) {
         bool new_max = false;
-        #pragma unroll 1
         for (int j = 0; j < 9; ++j) f[j] = st.FBest[j];  // the reference's `f` is whatever the last iteration left
         I = blk_rFtH(c, W, W.btmp[0], P.th, H, f, st.cur);
         int d;
         if (I > st.maxS.I) {
           blk_resid_F(c, P.metric, f, W.err[st.e[3]]);
           st.maxS.I = I;
-          #pragma unroll 1
           for (int j = 0; j < 9; ++j) st.F[j] = f[j];
           new_max = true;
           d = st.e[3];
@@ -680,7 +657,6 @@ DG_ENGN void ransac_F_pair(const Ctx& c, const FParams& P, Workspace& W, double*
 
   final_mask_F(c, P, W, st, mask_out);
   if (c.tid == 0) {
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i) F_out[i] = st.F[i];
     stats_out[0] = no_sam;
     stats_out[1] = st.iter_cnt;

@@ -79,7 +79,6 @@ DG_ENGN Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, in
 #endif
   if (maxS.I < 4) return S;
   S = blk_inlidxs(c, W.err[e[4]], th * kMWM, inl);
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) h[i] = Hio[i];
   blk_fit_H(c, inl, (int)S.I, h);
   #pragma unroll 1
@@ -96,7 +95,6 @@ DG_ENGN Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, in
       e[1] = e[0];
       e[0] = d;
       d = e[1];
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) Hio[i] = h[i];
     }
     if (S.I < 4) return maxS;
@@ -109,7 +107,6 @@ DG_ENGN Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, in
     maxS = S;
     e[1] = e[0];
     e[0] = d;
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i) Hio[i] = h[i];
   }
   return maxS;
@@ -124,7 +121,6 @@ DG_ENGN Score lo_inner_H(const Ctx& c, const HParams& P, Workspace& W, int* e, i
   if (ssiz > 12) ssiz = 12;
   int t = e[2]; e[2] = e[0]; e[0] = t;
   double h[9];
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) h[i] = Hout[i];
   #pragma unroll 1
   for (int rep = 0; rep < kRanRep; ++rep) {
@@ -137,7 +133,6 @@ DG_ENGN Score lo_inner_H(const Ctx& c, const HParams& P, Workspace& W, int* e, i
     if (score_less(maxS, S)) {
       maxS = S;
       t = e[2]; e[2] = e[0]; e[0] = t;
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) Hout[i] = h[i];
     }
   }
@@ -163,7 +158,13 @@ DG_ENGN bool run_lo_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, 
   blk_fit_H(c, W.inliers, (int)S.I, h);
   blk_resid_H(c, P.metric, h, W.err[d]);
   S = blk_inlidxs(c, W.err[d], P.th, W.inliers);
+#ifdef DG_TRACE_DEV
+  if (c.tid == 0) printf("LOH start ninl=%u J=%.12g\n", S.I, S.J);
+#endif
   S = lo_inner_H(c, P, W, st.e, W.inliers, (int)S.I, P.th, h, st.iterID, st.cur, st.ht);
+#ifdef DG_TRACE_DEV
+  if (c.tid == 0) printf("LOH end I=%u J=%.12g\n", S.I, S.J);
+#endif
   if (score_less(st.maxS, S) && !h_close_to_singular(h)) {
     bool do_update = true;
     if (P.do_sym) {
@@ -175,7 +176,6 @@ DG_ENGN bool run_lo_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, 
     if (do_update) {
       const int t = st.e[0]; st.e[0] = st.e[3]; st.e[3] = t;
       st.maxS = S;
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) st.H[i] = h[i];
       new_max = true;
     }
@@ -193,22 +193,25 @@ DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int k
   for (int k = kbeg + c.tid; k <= kend; k += c.nt) {
     int sel[4];
     minimal_sample<4>(P.seed, (uint32_t)k, c.N, sel);
-    double sx1[4], sy1[4], sx2[4], sy2[4], px1[4], py1[4], px2[4], py2[4];
-    #pragma unroll 1
+    // px*: sample in DRAW order (rows of the DLT system); sx*: the reference's samidx order (reverse) for the
+    // orientation test.  Both are filled with compile-time indices so they stay in registers.
+    double px1[4], py1[4], px2[4], py2[4], sx1[4], sy1[4], sx2[4], sy2[4];
+#pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int p = sel[t];
       px1[t] = c.x1[p]; py1[t] = c.y1[p]; px2[t] = c.x2[p]; py2[t] = c.y2[p];
+      sx1[3 - t] = px1[t]; sy1[3 - t] = py1[t]; sx2[3 - t] = px2[t]; sy2[3 - t] = py2[t];
     }
-    #pragma unroll 1
-    for (int t = 0; t < 4; ++t) { sx1[t] = px1[3 - t]; sy1[t] = py1[3 - t]; sx2[t] = px2[3 - t]; sy2[t] = py2[3 - t]; }
     if (!oriented_ok_H(sx1, sy1, sx2, sy2)) continue;
     double h[9];
     if (!h_from_4pt(px1, py1, px2, py2, h)) continue;
+#ifdef DG_TRACE_DEV
+    if (k <= 40) printf("WH2 k=%d h=%.10g %.10g %.10g sing=%d\n", k, h[0], h[4], h[8], (int)h_close_to_singular(h));
+#endif
     if (h_close_to_singular(h)) continue;
     const int slot = atomic_inc_shared(&c.sc->counter[0]);
     if (slot < W.cand_cap) {
       Cand& cd = W.cand[slot];
-      #pragma unroll 1
       for (int j = 0; j < 9; ++j) cd.f[j] = h[j];
       cd.k = k;
       cd.root = 0;
@@ -223,7 +226,6 @@ DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int k
     bool keep = passall;
     if (!passall) {
       double h[9];
-      #pragma unroll 1
       for (int j = 0; j < 9; ++j) h[j] = W.cand[ci].f[j];
       HSym s;
       if (P.metric != H_SAMPSON) h_sym_prepare(h, &s);
@@ -263,13 +265,15 @@ DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int k
 // REPLAY of one surviving iteration (exp_ranH.c:580-756).
 DG_ENGN void replay_iteration_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, int k, const Cand& cd) {
   double h[9];
-  #pragma unroll 1
   for (int j = 0; j < 9; ++j) h[j] = cd.f[j];
   st.cur.seed = P.seed; st.cur.k = (uint32_t)k; st.cur.j = 5;
   bool new_max = false, do_iterate;
   const int d = st.e[0];
   blk_resid_H(c, P.metric, h, W.err[d]);
   Score S = blk_inlidxs(c, W.err[d], P.th, W.itmp[0]);
+#ifdef DG_TRACE_DEV
+  if (c.tid == 0) printf("RH k=%d S.I=%u S.J=%.12g maxS.J=%.12g maxSs.J=%.12g iter=%d\n", k, S.I, S.J, st.maxS.J, st.maxSs.J, st.iter_cnt);
+#endif
   if (score_less(st.maxS, S)) {
     if (P.do_sym) {
       S.Is = blk_sym_count_H(c, h, W.itmp[0], (int)S.I, P.sym_th);
@@ -279,7 +283,6 @@ DG_ENGN void replay_iteration_H(const Ctx& c, const HParams& P, Workspace& W, HS
     st.e[3] = d;
     st.maxS = S;
     new_max = true;
-    #pragma unroll 1
     for (int j = 0; j < 9; ++j) st.H[j] = h[j];
   }
   if (score_less(st.maxSs, S)) {
@@ -305,15 +308,12 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
                                  int* stats_out) {
   HState st;
   st.maxS = make_score(); st.maxSs = make_score();
-  #pragma unroll 1
   for (int i = 0; i < 4; ++i) st.e[i] = i;
   st.e[4] = 3;
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) st.H[i] = 0.0;
   st.max_sam = P.max_iters; st.iter_cnt = 0; st.iterID = 0; st.no_rej = 0;
   st.ht.n = 0;
   st.cur.seed = P.seed; st.cur.k = 0; st.cur.j = 1;
-  #pragma unroll 1
   for (int r = 0; r < 4; ++r)
     #pragma unroll 1
     for (int j = c.tid; j < c.N; j += c.nt) W.err[r][j] = 0.0;
@@ -357,7 +357,6 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
   // post-loop LO if none ran (exp_ranH.c:759-862)
   if (st.iter_cnt == 0) {
     double h[9];
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i) h[i] = st.H[i];
     run_lo_H(c, P, W, st, h);
   }
@@ -378,7 +377,6 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
     DG_SYNC();
   }
   if (c.tid == 0) {
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i) H_out[i] = st.H[i];
     stats_out[0] = no_sam;
     stats_out[1] = st.iter_cnt;

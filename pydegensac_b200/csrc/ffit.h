@@ -110,7 +110,6 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
         const int p = idx[i];
         double row[9];
         f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], row);
-        #pragma unroll 1
         for (int r = 0; r < 9; ++r) ws->A[r * len + i] = row[r];
       }
       DG_WSYNC();
@@ -118,7 +117,6 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
         #pragma unroll 1
         for (int i = c.lane; i < len; i += W) {
           const double wi = w[idx[i]];
-          #pragma unroll 1
           for (int t = 0; t < 9; ++t) {
             const int lin = i + 9 * t;
             if (lin < 9 * len) ws->A[lin] *= wi;
@@ -132,10 +130,8 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
       if (!have && len > 0) warp_left_null_9xk(ws, len, c.lane, W);
       if (c.lane == 0) {
         double q[9];
-        #pragma unroll 1
         for (int i = 0; i < 9; ++i) q[i] = (len > 0) ? ws->cs[i] : ((i == 8) ? 1.0 : 0.0);
         enforce_rank2(q);
-        #pragma unroll 1
         for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
       }
     }
@@ -182,9 +178,7 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
         a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
         b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
         const double ww = w ? w[p] : 1.0;
-        #pragma unroll 1
         for (int k = 0; k < 3; ++k)
-          #pragma unroll 1
           for (int l = 0; l < 3; ++l) {
             double v = a[l] * b[k];
             if (w) v *= ww;
@@ -207,11 +201,9 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
       warp_smallest_eigvec9(ws, c.lane, W);
       if (c.lane == 0) {
         double q[9];
-        #pragma unroll 1
         for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
         enforce_rank2(q);
         denorm_F(q, A1, A2);
-        #pragma unroll 1
         for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
       }
     }
@@ -221,7 +213,6 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
   }
   // Hartley normalisation (reference normu, utools.c:7-51)
   double v[kVecRed];
-  #pragma unroll 1
   for (int i = 0; i < 4; ++i) v[i] = 0.0;
   #pragma unroll 1
   for (int j = c.tid; j < len; j += c.nt) {
@@ -256,14 +247,11 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
     double a[3], b[3], row[9];
     a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
     b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
-    #pragma unroll 1
     for (int k = 0; k < 3; ++k)
-      #pragma unroll 1
       for (int l = 0; l < 3; ++l) row[3 * k + l] = a[l] * b[k];
     const double ww = w ? w[p] : 1.0;
     if (w) for (int k = 0; k < 9; ++k) row[k] *= ww;
     int t = 0;
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i)
       #pragma unroll 1
       for (int jj = 0; jj <= i; ++jj) v[t++] += row[i] * row[jj];
@@ -274,11 +262,9 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
     warp_min_eigvec9_packed(ws, c.sc->vec_out, c.lane, DG_DEVICE_PASS ? 32 : 1);
     if (c.lane == 0) {
       double q[9];
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
       enforce_rank2(q);
       denorm_F(q, A1, A2);
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
     }
   }

@@ -39,7 +39,6 @@ DG_HDN void seven_pt_cubic(const double* A, double* B, double* p) {
          a23 * (-(a32 * b11) + a31 * b12 + a12 * b31 - 2 * b12 * b31 - a11 * b32 + 2 * b11 * b32) +
          (-(a12 * a21) + 2 * a21 * b12 + 2 * a12 * b21 - 3 * b12 * b21 - 2 * a11 * b22 + 3 * b11 * b22) * b33 +
          a22 * (a33 * b11 - a31 * b13 - a13 * b31 + 2 * b13 * b31 + a11 * b33 - 2 * b11 * b33);
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) B[i] = A[i] - B[i];
   b11 = B[0]; b12 = B[1]; b13 = B[2]; b21 = B[3]; b22 = B[4]; b23 = B[5]; b31 = B[6]; b32 = B[7]; b33 = B[8];
   p[3] = -(b13 * b22 * b31) + b12 * b23 * b31 + b13 * b21 * b32 - b11 * b23 * b32 - b12 * b21 * b33 + b11 * b22 * b33;
@@ -88,7 +87,6 @@ DG_HD bool oriented_ok_F(const double* F, const double* sx1, const double* sy1, 
   double ec[3];
   cross3(ec, F, F + 6);
   bool big = false;
-  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
     if ((ec[i] > xeps) || (ec[i] < -xeps)) big = true;
   if (!big) cross3(ec, F + 3, F + 6);

@@ -20,13 +20,11 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
     DG_SYNC();
     if (c.tid == 0) {
       double px1[4], py1[4], px2[4], py2[4], hh[9];
-      #pragma unroll 1
       for (int i = 0; i < 4; ++i) {
         const int p = idx[i];
         px1[i] = c.x1[p]; py1[i] = c.y1[p]; px2[i] = c.x2[p]; py2[i] = c.y2[p];
       }
       h_from_4pt_u2h_quirk(px1, py1, px2, py2, hh);
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) c.sc->bc[i] = hh[i];
     }
     bc_fetch(c, h, 9);
@@ -69,7 +67,6 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
         b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
         double* r0 = rows + 18 * j;
         double* r1 = r0 + 9;
-        #pragma unroll 1
         for (int t = 0; t < 3; ++t) {
           r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
           r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
@@ -91,10 +88,8 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
       warp_smallest_eigvec9(ws, c.lane, W);
       if (c.lane == 0) {
         double q[9];
-        #pragma unroll 1
         for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
         denorm_H(q, A1, A2);
-        #pragma unroll 1
         for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
       }
     }
@@ -102,7 +97,6 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
     return;
   }
   double v[kVecRed];
-  #pragma unroll 1
   for (int i = 0; i < 4; ++i) v[i] = 0.0;
   #pragma unroll 1
   for (int j = c.tid; j < len; j += c.nt) {
@@ -136,13 +130,11 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
     double a[3], b[3], r0[9], r1[9];
     a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
     b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
-    #pragma unroll 1
     for (int t = 0; t < 3; ++t) {  // reference lin_hgN, Htools.c:60-99
       r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
       r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
     }
     int t = 0;
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i)
       #pragma unroll 1
       for (int jj = 0; jj <= i; ++jj) {
@@ -157,10 +149,8 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
     warp_min_eigvec9_packed(ws, c.sc->vec_out, c.lane, DG_DEVICE_PASS ? 32 : 1);
     if (c.lane == 0) {
       double q[9];
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
       denorm_H(q, A1, A2);
-      #pragma unroll 1
       for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
     }
   }

@@ -32,7 +32,6 @@ DG_HD void h_pinvJ(double a, double b, double c, double d, double e, double* pJ)
   pJ[6] = pJ[3];
   pJ[7] = c * (a2 + b2 + c2);
   const double N = a * pJ[0] + b * pJ[1] + c * pJ[2];
-  #pragma unroll 1
   for (int i = 0; i < 8; ++i) pJ[i] /= N;
 }
 
@@ -60,7 +59,6 @@ DG_HD double h_resid_sampson(const double* H, double x1, double y1, double x2, d
   double pJ[8];
   h_pinvJ(a, b, c, d, e, pJ);
   double p = 0.0;
-  #pragma unroll 1
   for (int j = 0; j < 4; ++j) {
     const double t = pJ[j] * r1 + pJ[j + 4] * r2;
     p += t * t;
@@ -75,7 +73,6 @@ DG_HDN void h_sym_prepare(const double* H, HSym* s) {
   s->Hi[0] = H[0]; s->Hi[1] = H[3]; s->Hi[2] = H[6];
   s->Hi[3] = H[1]; s->Hi[4] = H[4]; s->Hi[5] = H[7];
   s->Hi[6] = H[2]; s->Hi[7] = H[5]; s->Hi[8] = H[8];
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) s->H1[i] = s->Hi[i];
   inv3(s->H1);
 }
@@ -116,7 +113,6 @@ DG_HD double h_resid_symmax_gate(const HSym& s, double x1, double y1, double x2,
 // reference's samidx order a,b,c,d.
 DG_HD bool oriented_ok_H(const double* sx1, const double* sy1, const double* sx2, const double* sy2) {
   double A[4][3], B[4][3], p[3], q[3];
-  #pragma unroll 1
   for (int i = 0; i < 4; ++i) {
     A[i][0] = sx1[i]; A[i][1] = sy1[i]; A[i][2] = 1.0;
     B[i][0] = sx2[i]; B[i][1] = sy2[i]; B[i][2] = 1.0;
@@ -137,7 +133,6 @@ DG_HD bool h_close_to_singular(const double* h) {
   const double v = det3(h);
   double tol = h[8];
   if (tol == 0) {
-    #pragma unroll 1
     for (int i = 0; i < 9; ++i) tol += h[i] * h[i];
     tol = sqrt(tol);
     tol *= 0.001;
@@ -166,12 +161,9 @@ DG_HD void denorm_H(double* F, const double* A1, const double* A2) {
 // Points are given in DRAW order.  Returns false unless the null space is one-dimensional.
 DG_HDN bool h_from_4pt(const double* px1, const double* py1, const double* px2, const double* py2, double* h) {
   double M[81], sol[81];
-  #pragma unroll 1
   for (int i = 0; i < 4; ++i) h_lin_rows(px1[i], py1[i], px2[i], py2[i], M + 18 * i, M + 18 * i + 9);
-  #pragma unroll 1
   for (int i = 72; i < 81; ++i) M[i] = 0.0;
   const int ns = nullspace9(M, sol);
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) h[i] = sol[i];
   return ns == 1;
 }
@@ -185,21 +177,15 @@ DG_HDN void h_from_4pt_u2h_quirk(const double* px1, const double* py1, const dou
   double Z[81], T[81], sol[81];
   #pragma unroll 1
   for (int i = 0; i < 81; ++i) { Z[i] = 0.0; sol[i] = 0.0; }
-  #pragma unroll 1
   for (int i = 0; i < 4; ++i) {
     double r0[9], r1[9];
     h_lin_rows(px1[i], py1[i], px2[i], py2[i], r0, r1);
-    #pragma unroll 1
     for (int c = 0; c < 9; ++c) { Z[8 * c + 2 * i] = r0[c]; Z[8 * c + 2 * i + 1] = r1[c]; }
   }
-  #pragma unroll 1
   for (int r = 0; r < 9; ++r)
-    #pragma unroll 1
     for (int c = 0; c < 9; ++c) T[9 * r + c] = Z[9 * c + r];
-  #pragma unroll 1
   for (int i = 72; i < 81; ++i) T[i] = 0.0;
   nullspace9(T, sol);
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) h[i] = sol[i];
 }
 

@@ -16,7 +16,6 @@ DG_HDN int nullspace9(double* M, double* ns) {
   const double tol = 1e-12;
   int freec[9], pivc[9];
   int nfree = 0, npiv = 0, row = 0;
-  #pragma unroll 1
   for (int col = 0; col < 9; ++col) {
     int best = row;
     double mag = fabs(M[9 * row + col]);
@@ -43,7 +42,6 @@ DG_HDN int nullspace9(double* M, double* ns) {
     const double p = M[9 * row + col];
     #pragma unroll 1
     for (int c = col; c < 9; ++c) M[9 * row + c] /= p;
-    #pragma unroll 1
     for (int r = 0; r < 9; ++r) {
       if (r == row) continue;
       const double a = M[9 * r + col];
@@ -71,19 +69,16 @@ DG_HDN int nullspace9(double* M, double* ns) {
 DG_HDN void jacobi_eig9(double* A, double* V, double* d) {
   #pragma unroll 1
   for (int i = 0; i < 81; ++i) V[i] = 0.0;
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) V[i * 10] = 1.0;
   #pragma unroll 1
   for (int sweep = 0; sweep < 40; ++sweep) {
     double off = 0.0, dia = 0.0;
-    #pragma unroll 1
     for (int p = 0; p < 9; ++p) {
       dia += A[p * 10] * A[p * 10];
       #pragma unroll 1
       for (int q = p + 1; q < 9; ++q) off += A[p * 9 + q] * A[p * 9 + q];
     }
     if (!(off > 4e-30 * dia) || off == 0.0) break;  // off-norm at rounding level: converged
-    #pragma unroll 1
     for (int p = 0; p < 8; ++p) {
       #pragma unroll 1
       for (int q = p + 1; q < 9; ++q) {
@@ -93,19 +88,16 @@ DG_HDN void jacobi_eig9(double* A, double* V, double* d) {
         const double theta = (aqq - app) / (2.0 * apq);
         const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
         const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        #pragma unroll 1
         for (int k = 0; k < 9; ++k) {  // columns p,q
           const double akp = A[k * 9 + p], akq = A[k * 9 + q];
           A[k * 9 + p] = c * akp - s * akq;
           A[k * 9 + q] = s * akp + c * akq;
         }
-        #pragma unroll 1
         for (int k = 0; k < 9; ++k) {  // rows p,q
           const double apk = A[p * 9 + k], aqk = A[q * 9 + k];
           A[p * 9 + k] = c * apk - s * aqk;
           A[q * 9 + k] = s * apk + c * aqk;
         }
-        #pragma unroll 1
         for (int k = 0; k < 9; ++k) {
           const double vkp = V[k * 9 + p], vkq = V[k * 9 + q];
           V[k * 9 + p] = c * vkp - s * vkq;
@@ -114,7 +106,6 @@ DG_HDN void jacobi_eig9(double* A, double* V, double* d) {
       }
     }
   }
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) d[i] = A[i * 10];
 }
 
@@ -123,10 +114,8 @@ DG_HDN void min_eigvec9(double* C, double* v) {
   double V[81], d[9];
   jacobi_eig9(C, V, d);
   int j = 0;
-  #pragma unroll 1
   for (int i = 1; i < 9; ++i)
     if (d[i] < d[j]) j = i;
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) v[i] = V[i * 9 + j];
 }
 
@@ -187,9 +176,7 @@ DG_HDN void enforce_rank2(double* F) {
   int m = 0;
   if (sv[1] < sv[m]) m = 1;
   if (sv[2] < sv[m]) m = 2;
-  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
-    #pragma unroll 1
     for (int j = 0; j < 3; ++j) F[3 * i + j] -= G[3 * i + m] * V[3 * j + m];
 }
 
@@ -213,7 +200,6 @@ DG_HDN void right_null3(const double* A, double* v) {
 // ---------------------------------------------------------------------------------------------
 DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
   double a[9], d[3], e[2], V[9];
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) a[i] = Ain[i];
   e[0] = e[1] = 0.0;
   // --- column 0 reflector
@@ -226,7 +212,6 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
       s += a[0] * h;
       s = 1. / s;
       w0 += h;
-      #pragma unroll 1
       for (int k = 1; k < 3; ++k) {
         double r = w0 * a[k] + w1 * a[3 + k] + w2 * a[6 + k];
         r *= s;
@@ -247,7 +232,6 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
       s = 1. / s;
       const double p0 = a[1] + h;
       const double t = 1. / p0;
-      #pragma unroll 1
       for (int row = 1; row < 3; ++row) {
         double r = p0 * a[3 * row + 1] + a[2] * a[3 * row + 2];
         r *= s;
@@ -276,7 +260,6 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
   }
   e[1] = a[5];
   d[2] = a[8];
-  #pragma unroll 1
   for (int i = 0; i < 9; ++i) V[i] = 0.0;
   V[0] = 1.0; V[4] = 1.0; V[8] = 1.0;
   if (hb != 0.) {
@@ -289,7 +272,6 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
   // --- implicit-shift QR sweeps on the bidiagonal (d,e)
   int m = 3;
   double t = fabs(d[0]);
-  #pragma unroll 1
   for (int j = 1; j < 3; ++j) {
     const double s = fabs(d[j]) + fabs(e[j - 1]);
     if (s > t) t = s;
@@ -333,7 +315,6 @@ DG_HDN void gkr_third_right_vector3(const double* Ain, double* vout) {
         }
         aa = c * y + s * bb;
         bb = c * bb - s * y;
-        #pragma unroll 1
         for (int r = 0; r < 3; ++r) {
           const double w = c * V[3 * r + i] + s * V[3 * r + i + 1];
           V[3 * r + i + 1] = c * V[3 * r + i + 1] - s * V[3 * r + i];
@@ -370,7 +351,6 @@ DG_HDN void left_null_9xk(double* Z, int len, double* q) {
     #pragma unroll 1
     for (int r = c; r < 9; ++r) nrm += Z[r * len + c] * Z[r * len + c];
     nrm = sqrt(nrm);
-    #pragma unroll 1
     for (int r = 0; r < 9; ++r) vs[c][r] = 0.0;
     if (nrm == 0.0) { beta[c] = 0.0; continue; }
     const double x0 = Z[c * len + c];
@@ -392,7 +372,6 @@ DG_HDN void left_null_9xk(double* Z, int len, double* q) {
       for (int r = c; r < 9; ++r) Z[r * len + cc] -= dot * vs[c][r];
     }
   }
-  #pragma unroll 1
   for (int r = 0; r < 9; ++r) q[r] = 0.0;
   q[8] = 1.0;
   #pragma unroll 1
@@ -411,12 +390,9 @@ DG_HDN void left_null_9xk(double* Z, int len, double* q) {
 // matutls/minv.c:11,27), in which case the matrix content is unspecified.
 DG_HDN int inv3(double* a) {
   double m[3][6];
-  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
-    #pragma unroll 1
     for (int j = 0; j < 3; ++j) { m[i][j] = a[3 * i + j]; m[i][3 + j] = (i == j) ? 1.0 : 0.0; }
   double tq = 0.0;
-  #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
     int best = c;
     double s = fabs(m[c][c]);
@@ -428,22 +404,16 @@ DG_HDN int inv3(double* a) {
     tq = tq > s ? tq : s;
     if (s < 1e-15 * tq || s == 0.0) return -1;
     if (best != c)
-      #pragma unroll 1
       for (int k = 0; k < 6; ++k) { const double t = m[c][k]; m[c][k] = m[best][k]; m[best][k] = t; }
     const double inv = 1.0 / m[c][c];
-    #pragma unroll 1
     for (int k = 0; k < 6; ++k) m[c][k] *= inv;
-    #pragma unroll 1
     for (int r = 0; r < 3; ++r) {
       if (r == c) continue;
       const double f = m[r][c];
-      #pragma unroll 1
       for (int k = 0; k < 6; ++k) m[r][k] -= f * m[c][k];
     }
   }
-  #pragma unroll 1
   for (int i = 0; i < 3; ++i)
-    #pragma unroll 1
     for (int j = 0; j < 3; ++j) a[3 * i + j] = m[i][3 + j];
   return 0;
 }

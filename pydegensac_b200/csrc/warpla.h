@@ -68,7 +68,6 @@ DG_ENGN void warp_jacobi_eig9(WarpScratch* ws, int lane, int W) {
     off = wl_sum(off);
     dia = wl_sum(dia);
     if (!(off > 4e-30 * dia) || off == 0.0) break;  // off-norm at rounding level: converged
-    #pragma unroll 1
     for (int r = 0; r < 9; ++r) {
       #pragma unroll 1
       for (int k = lane; k < 4; k += W) {
@@ -165,7 +164,6 @@ DG_ENGN void warp_smallest_eigvec9(WarpScratch* ws, int lane, int W) {
   bool ok = (fro > 0.0) && (fro == fro) && (fro < 1e300);
   const double tiny = sqrt(fro) * 1e-30;
   if (ok) {
-#pragma unroll 1
     for (int k = 0; k < 9; ++k) {
       double dk = L[k * 10];
       if (!(dk > tiny)) dk = tiny;          // exactly singular / rounding-negative pivot: regularise
@@ -199,7 +197,6 @@ DG_ENGN void warp_smallest_eigvec9(WarpScratch* ws, int lane, int W) {
 #pragma unroll 1
       for (int i = lane; i < 9; i += W) y[i] = x[i];
       DG_WSYNC();
-#pragma unroll 1
       for (int k = 0; k < 8; ++k) {          // forward substitution with the unit lower factor
 #pragma unroll 1
         for (int i = k + 1 + lane; i < 9; i += W) y[i] -= L[i * 9 + k] * y[k];
@@ -309,7 +306,6 @@ DG_ENGN bool warp_null_8x9(WarpScratch* ws, int lane, int W) {
   }
   DG_WSYNC();
   bool ok = true;
-#pragma unroll 1
   for (int col = 0; col < 8; ++col) {
     if (lane == 0) {
       int best = col;
@@ -373,7 +369,6 @@ DG_ENGN void warp_left_null_9xk(WarpScratch* ws, int len, int lane, int W) {
       #pragma unroll 1
       for (int r = c; r < 9; ++r) nrm += Z[r * len + c] * Z[r * len + c];
       nrm = sqrt(nrm);
-      #pragma unroll 1
       for (int r = 0; r < 9; ++r) vs[c * 9 + r] = 0.0;
       if (nrm == 0.0) {
         beta[c] = 0.0;
@@ -405,7 +400,6 @@ DG_ENGN void warp_left_null_9xk(WarpScratch* ws, int len, int lane, int W) {
   }
   if (lane == 0) {
     double q[9];
-    #pragma unroll 1
     for (int r = 0; r < 9; ++r) q[r] = 0.0;
     q[8] = 1.0;
     #pragma unroll 1
@@ -417,7 +411,6 @@ DG_ENGN void warp_left_null_9xk(WarpScratch* ws, int len, int lane, int W) {
       #pragma unroll 1
       for (int r = c; r < 9; ++r) q[r] -= dot * vs[c * 9 + r];
     }
-    #pragma unroll 1
     for (int r = 0; r < 9; ++r) ws->cs[r] = q[r];
   }
   DG_WSYNC();

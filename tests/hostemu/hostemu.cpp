@@ -27,7 +27,10 @@ struct Emu {
   double* soa;
 };
 
+static int g_poison = 0;
+extern "C" void emu_set_poison(int v) { g_poison = v; }
 static void emu_setup(Emu& E, const double* x1y1, const double* x2y2, int n, int dim, int chunk) {
+  memset(&E.sc, g_poison, sizeof(E.sc));
   const size_t bytes = workspace_bytes(n, chunk);
   E.slab = (unsigned char*)calloc(bytes + 256, 1);
   workspace_carve(E.slab, n, chunk, &E.W, &E.soa);
