@@ -27,7 +27,13 @@ __device__ unsigned long long g_dg_prof[32];
 
 namespace {
 
-constexpr int kMaxThreads = 256;
+#ifndef DG_LB_THREADS
+#define DG_LB_THREADS 256
+#endif
+#ifndef DG_LB_BLOCKS
+#define DG_LB_BLOCKS 2
+#endif
+constexpr int kMaxThreads = DG_LB_THREADS;
 constexpr int kChunk = 512;
 
 // CTA shape.  256 threads x 2 CTAs per SM measured fastest on B200 (profiles/README.md): the waves and the O(N)
@@ -70,7 +76,7 @@ struct BatchArgs {
 };
 
 template <int KIND>  // 0: fundamental matrix, 1: homography
-__global__ void __launch_bounds__(kMaxThreads, 2) ransac_pairs_kernel(BatchArgs a) {
+__global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel(BatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_pair;
   dg::BlockScratch* sc = reinterpret_cast<dg::BlockScratch*>(smem_raw);

@@ -1,0 +1,36 @@
+"""The wave's FP32 upper-bound MSAC score (csrc/filter32.h) must never under-estimate the exact FP64 score and
+must not change any result.  Checked through the one-thread host emulation, which is compiled with
+DG_FILTER_CHECK: every model scored by the filter is also scored in FP64 and compared."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from pydegensac_b200.scenes import scene_F
+
+
+def _stats(E):
+    ck = ctypes.c_long(); vi = ctypes.c_long(); ms = ctypes.c_double()
+    E.emu_filter_stats(ctypes.byref(ck), ctypes.byref(vi), ctypes.byref(ms))
+    return ck.value, vi.value, ms.value
+
+
+@pytest.mark.parametrize("scale", [1.0, 8.0, 0.05])
+def test_upper_bound_holds_and_results_unchanged(scale):
+    from tests.hostemu import emu
+    E = emu.lib()
+    c0, v0, _ = _stats(E)
+    for sc in range(4):
+        for plane in (0.0, 0.8):
+            for et in (0, 1):
+                p1, p2, _ = scene_F(1500, 0.3, 100 + sc, plane)
+                p1 = p1 * scale + 1000.0 * (scale - 1.0)      # other coordinate scales and large offsets
+                p2 = p2 * scale - 300.0 * (scale - 1.0)
+                kw = dict(px_th=1.0 * scale, conf=0.9999, max_iters=3000, error_type=et, seed=sc)
+                E.emu_set_filter32(1); a = emu.find_fundamental(p1, p2, **kw)
+                E.emu_set_filter32(0); b = emu.find_fundamental(p1, p2, **kw)
+                E.emu_set_filter32(1)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    c1, v1, slack = _stats(E)
+    assert c1 - c0 > 2000, "filter was not exercised"
+    assert v1 - v0 == 0, "FP32 bound fell below the FP64 score %d times" % (v1 - v0)
