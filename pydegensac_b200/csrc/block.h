@@ -123,10 +123,34 @@ DG_ENG inline void bc_fetch(const Ctx& c, double* dst, int n) {
   DG_SYNC();
 }
 
+// Exclusive scan of an int and sum of a double over the CTA in ONE barrier pair (both results to every thread).
+DG_ENG inline void blk_scan_sum(const Ctx& c, int cnt, double J, int* off, int* total, double* Jtot) {
+  const int incl = warp_incl_scan_i(cnt, c.lane);
+  const double js = warp_sum(J);
+  DG_SYNC();
+  if (c.lane == 31 || c.tid == c.nt - 1) c.sc->red_i[c.wid] = incl;
+  if (c.lane == 0) c.sc->red_d[c.wid] = js;
+  DG_SYNC();
+  int base = 0, tot = 0;
+  double jt = 0.0;
+  for (int w = 0; w < c.nw; ++w) {
+    const int t = c.sc->red_i[w];
+    if (w < c.wid) base += t;
+    tot += t;
+    jt += c.sc->red_d[w];
+  }
+  *off = base + incl - cnt;
+  *total = tot;
+  *Jtot = jt;
+}
+
 // MSAC score + ascending inlier index list of a residual row (reference inlidxs, rtools.c:160-171):
-// J = sum truncQuad(err, th), list = {i : err[i] <= th}.  Threads own contiguous index segments so the
-// list comes out ordered after one block scan.
+// J = sum truncQuad(err, th), list = {i : err[i] <= th}.  Threads own contiguous index segments so the list comes
+// out ordered after one block scan; up to 8 residuals per thread stay in registers between counting and writing
+// (one global read of the row, two barriers).
 DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list) {
+  DG_PROF_BEGIN(21);
+  DG_PROF_COUNT(22, 1);
   const int per = (c.N + c.nt - 1) / c.nt;
   const int beg = c.tid * per;
   const int end = (beg + per < c.N) ? beg + per : c.N;
@@ -135,21 +159,41 @@ DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list)
   // MSAC gain 1 - e/(9 th / 4) (reference truncQuad, rtools.c:228-236) with the division hoisted out of the loop
   const double wq = th * 9 / 4;
   const double winv = (th == 0) ? 0.0 : 1.0 / wq;
-  #pragma unroll 1
-  for (int i = beg; i < end; ++i) {
-    const double e = err[i];
-    if (th != 0 && e < wq) J += 1 - e * winv;
-    if (e <= th) ++cnt;
-  }
-  int total;
-  int off = blk_excl_scan_i(c, cnt, &total);
-  #pragma unroll 1
-  for (int i = beg; i < end; ++i)
-    if (err[i] <= th) list[off++] = i;
   Score s = make_score();
-  s.J = blk_sum(c, J);
+  int off, total;
+  double Jtot;
+  if (per <= 8) {
+    double e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = beg + j;
+      e[j] = (i < end) ? err[i] : INFINITY;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (th != 0 && !(e[j] >= wq)) J += 1 - e[j] * winv;   // NaN -> NaN score, as the reference's truncQuad
+      if (e[j] <= th) ++cnt;
+    }
+    blk_scan_sum(c, cnt, J, &off, &total, &Jtot);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (e[j] <= th) list[off++] = beg + j;
+  } else {
+    #pragma unroll 1
+    for (int i = beg; i < end; ++i) {
+      const double e = err[i];
+      if (th != 0 && !(e >= wq)) J += 1 - e * winv;
+      if (e <= th) ++cnt;
+    }
+    blk_scan_sum(c, cnt, J, &off, &total, &Jtot);
+    #pragma unroll 1
+    for (int i = beg; i < end; ++i)
+      if (err[i] <= th) list[off++] = i;
+  }
+  s.J = Jtot;
   s.I = (unsigned)total;
   DG_SYNC();
+  DG_PROF_END(21);
   return s;
 }
 

@@ -33,7 +33,7 @@
 
 // Optional phase profiling (build with -DDG_PROF): thread 0 of every CTA accumulates clock64() deltas.
 #if defined(DG_PROF) && DG_DEVICE_PASS
-extern __device__ unsigned long long g_dg_prof[32];
+extern __device__ unsigned long long g_dg_prof[64];
 #define DG_PROF_BEGIN(id) long long prof_t_##id = (threadIdx.x == 0) ? clock64() : 0
 #define DG_PROF_END(id) do { if (threadIdx.x == 0) atomicAdd(&g_dg_prof[id], (unsigned long long)(clock64() - prof_t_##id)); } while (0)
 #define DG_PROF_COUNT(id, n) do { if (threadIdx.x == 0) atomicAdd(&g_dg_prof[id], (unsigned long long)(n)); } while (0)

@@ -379,6 +379,7 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
   #pragma unroll 1
   for (unsigned rep = 0; rep < 15; ++rep) {
     // dual_sample: fresh identity permutations, `pos <-> rand()%len` swaps (DegUtils.c:596-632)
+    DG_PROF_BEGIN(36);
     DG_SYNC();
     if (c.tid == 0) {
       DrawCursor t = cur;
@@ -413,6 +414,7 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
     }
     cur.j += 10;
     DG_SYNC();
+    DG_PROF_END(36);
     double aF[9];
     blk_fit_F(c, usam, 10, nullptr, aF);
     blk_resid_F(c, F_SAMPSON, aF, Ds);
@@ -434,7 +436,8 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
     }
     if (no_i > max_s) {
       max_s = no_i;
-      no_i = blk_u2Fit(c, W, aF, v, th, th * 3, 4);
+      DG_PROF_COUNT(38, 1);
+      { DG_PROF_BEGIN(37); no_i = blk_u2Fit(c, W, aF, v, th, th * 3, 4); DG_PROF_END(37); }
       if (max_i < no_i) {
         #pragma unroll 1
         for (int i = c.tid; i < c.N; i += c.nt) inl[i] = v[i];
@@ -506,6 +509,7 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
     if (nw > WAVE) nw = WAVE;
     if (nw > 128) nw = 128;
     // thread 0 advances the persistent permutation speculatively for nw iterations
+    DG_PROF_BEGIN(32);
     DG_SYNC();
     if (c.tid == 0) {
       DrawCursor t = cur;
@@ -543,6 +547,8 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
     #pragma unroll 1
     for (int s = 0; s < nw; ++s)
       if ((unsigned)counts[s] > m_i) { ev = s; break; }
+    DG_PROF_END(32);
+    DG_PROF_COUNT(35, nw);
     if (ev < 0) {
       cur.j += 2u * (uint32_t)nw;
       no_sam += (unsigned)nw;
@@ -583,7 +589,8 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
       DG_SYNC();
       m_i = (unsigned)no_i;
       double Fnew[9];
-      blk_inner_FH(c, W, uHl, nH, uV, no_i, th, Fnew, inl, cur);
+      DG_PROF_COUNT(33, 1);
+      { DG_PROF_BEGIN(34); blk_inner_FH(c, W, uHl, nH, uV, no_i, th, Fnew, inl, cur); DG_PROF_END(34); }
       int cnt = 0, cnt2 = 0;
       #pragma unroll 1
       for (int i = c.tid; i < c.N; i += c.nt) {

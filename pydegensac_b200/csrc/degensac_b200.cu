@@ -22,7 +22,7 @@
 #include "workspace.h"
 
 #ifdef DG_PROF
-__device__ unsigned long long g_dg_prof[32];
+__device__ unsigned long long g_dg_prof[64];
 #endif
 
 namespace {
@@ -224,6 +224,7 @@ int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, doub
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   if (per_sm < 1) return fail(DGB200_E_CUDA, "kernel does not fit on an SM");
+  if (const char* e = getenv("DGB200_CTAS_PER_SM")) { const int cap = atoi(e); if (cap >= 1 && cap < per_sm) per_sm = cap; }
   int grid = g_c.sm_count * per_sm;     // persistent CTAs: a whole number of CTAs per SM
   if (grid > n_pairs) grid = n_pairs;
   a.ws_stride = dg::align_up(dg::workspace_bytes(n, kChunk), 256);
@@ -383,8 +384,8 @@ long long dgb200_kernel_launches(void) { return g_launches; }
 double dgb200_last_kernel_ms(void) { return g_last_ms; }
 #ifdef DG_PROF
 void dgb200_prof_read(unsigned long long* out, int reset) {
-  cudaMemcpyFromSymbol(out, g_dg_prof, sizeof(unsigned long long) * 32);
-  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_dg_prof, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(out, g_dg_prof, sizeof(unsigned long long) * 64);
+  if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_dg_prof, z, sizeof(z)); }
 }
 #endif
 void dgb200_release(void) {

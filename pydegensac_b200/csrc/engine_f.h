@@ -459,6 +459,8 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
                                       int cnt) {
   bool new_max = false, do_iterate = false;
   DG_PROF_BEGIN(2);
+  DG_PROF_COUNT(14, 1);
+  DG_PROF_COUNT(15, cnt);
   int sel[7], samidx[7];
   minimal_sample<7>(P.seed, (uint32_t)k, c.N, sel);
   for (int t = 0; t < 7; ++t) samidx[t] = sel[6 - t];
@@ -490,6 +492,7 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
       fprintf(stderr, "BS k=%d root=%d S.I=%u S.J=%.17g maxS.J=%.17g\n", k, i, S.I, S.J, st.maxS.J);
 #endif
       st.maxSs = S;
+      DG_PROF_COUNT(16, 1);
       bool degenerate = false;
       double H[9];
       if (P.degen) {
@@ -507,10 +510,12 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
         blk_resid_H_sampson(c, H, W.dtmp[4]);
         unsigned I = (unsigned)blk_count_lt(c, W.dtmp[4], P.th * 3);
         if (I < 8) { DG_PROF_END(6); break; }
-        I = blk_inner_H(c, W, H, 16 * P.th, 10, W.btmp[0], st.cur);
+        { DG_PROF_BEGIN(25); I = blk_inner_H(c, W, H, 16 * P.th, 10, W.btmp[0], st.cur); DG_PROF_END(25); }
+        DG_PROF_COUNT(30, 1);
         if ((int)I > st.Ihmax) st.Ihmax = (int)I;
         if (I > 6) {
-          I = blk_rFtH(c, W, W.btmp[0], P.th, H, f, st.cur);
+          { DG_PROF_BEGIN(26); I = blk_rFtH(c, W, W.btmp[0], P.th, H, f, st.cur); DG_PROF_END(26); }
+          DG_PROF_COUNT(31, 1);
           if (I > st.maxS.I) {
             blk_resid_F(c, P.metric, f, W.err[st.e[3]]);
             st.maxS.I = I;
@@ -544,6 +549,7 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
   }
   if (k == kIterSam && st.non_degen) do_iterate = true;
   if (do_iterate) {
+    DG_PROF_COUNT(17, 1);
     if (run_lo_F(c, P, W, st, W.err[st.e[4]])) new_max = true;
     if (new_max) {
       const int new_sam = nsamples((int)st.maxS.I + 1, c.N, 7, P.conf);
@@ -599,7 +605,7 @@ DG_ENGN void ransac_F_pair(const Ctx& c, const FParams& P, Workspace& W, double*
       pos += cnt;
       if (k >= st.max_sam) { finished = true; no_sam = k; break; }
       const double Tn = st.maxS.J < st.maxSs.J ? st.maxS.J : st.maxSs.J;
-      if (Tn < T && k < kend) { rewave = true; k0 = k; break; }
+      if (Tn < T && k < kend) { rewave = true; k0 = k; DG_PROF_COUNT(18, 1); break; }
     }
     if (finished) break;
     if (rewave) continue;

@@ -46,10 +46,15 @@ struct FParams {
 
 // ------------------------------------------------------------------ block-wide passes over the pair
 DG_ENGN void blk_resid_F(const Ctx& c, int metric, const double* F, double* out) {
+  DG_PROF_BEGIN(19);
+  DG_PROF_COUNT(20, 1);
   for (int i = c.tid; i < c.N; i += c.nt) out[i] = f_resid(metric, F, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
   DG_SYNC();
+  DG_PROF_END(19);
 }
 DG_ENGN void blk_resid_w_F(const Ctx& c, int metric, const double* F, double* out, double* w) {
+  DG_PROF_BEGIN(19);
+  DG_PROF_COUNT(20, 1);
   #pragma unroll 1
   for (int i = c.tid; i < c.N; i += c.nt) {
     double e, ww;
@@ -58,6 +63,7 @@ DG_ENGN void blk_resid_w_F(const Ctx& c, int metric, const double* F, double* ou
     w[i] = ww;
   }
   DG_SYNC();
+  DG_PROF_END(19);
 }
 // symmetric-epipolar consistency count over an index list (gate at exp_ranF.c:1383-1392)
 DG_ENGN unsigned blk_sym_count_F(const Ctx& c, const double* F, const int* list, int n, double sym_th) {
@@ -73,6 +79,7 @@ DG_ENGN unsigned blk_sym_count_F(const Ctx& c, const double* F, const int* list,
 // Partial Fisher-Yates permutation of list[0..max_sz) drawing `siz` slots; the subset is the last
 // `siz` entries (reference randsubset, rtools.c:25-39).  Sequential by nature: thread 0.
 DG_ENGN void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCursor& cur) {
+  DG_PROF_BEGIN(23);
   DG_SYNC();
   if (c.tid == 0) {
     DrawCursor t = cur;
@@ -87,6 +94,7 @@ DG_ENGN void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCu
   }
   cur.j += (uint32_t)siz;
   DG_SYNC();
+  DG_PROF_END(23);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -101,6 +109,7 @@ DG_ENGN void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCu
 DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, double* f) {
   if (len <= 8) {
     DG_PROF_BEGIN(7);
+    DG_PROF_COUNT(27, 1);
     DG_SYNC();
     if (c.wid == 0) {   // warp 0: one lane per column of the 9 x len system, Householder QR across the lanes
       WarpScratch* ws = &c.sc->ws[0];
@@ -131,7 +140,7 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
       if (c.lane == 0) {
         double q[9];
         for (int i = 0; i < 9; ++i) q[i] = (len > 0) ? ws->cs[i] : ((i == 8) ? 1.0 : 0.0);
-        enforce_rank2(q);
+        { DG_PROF_BEGIN(24); enforce_rank2(q); DG_PROF_END(24); }
         for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
       }
     }
@@ -140,6 +149,7 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
     return;
   }
   DG_PROF_BEGIN(8);
+  DG_PROF_COUNT(28, 1);
   if (len <= 32) {
     // Small support (the 9..14-point inner LO samples, 10-point plane+parallax samples): the whole fit runs
     // inside warp 0 -- one lane per correspondence, no block-wide reduction, rows kept in shared memory.
@@ -198,11 +208,11 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
         ws->A[9 * jj + i] = s;
       }
       DG_WSYNC();
-      warp_smallest_eigvec9(ws, c.lane, W);
+      { DG_PROF_BEGIN(29); warp_smallest_eigvec9(ws, c.lane, W); DG_PROF_END(29); }
       if (c.lane == 0) {
         double q[9];
         for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
-        enforce_rank2(q);
+        { DG_PROF_BEGIN(24); enforce_rank2(q); DG_PROF_END(24); }
         denorm_F(q, A1, A2);
         for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
       }
@@ -212,6 +222,8 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
     return;
   }
   // Hartley normalisation (reference normu, utools.c:7-51)
+  DG_PROF_BEGIN(40);
+  DG_PROF_COUNT(39, 1);
   double v[kVecRed];
   for (int i = 0; i < 4; ++i) v[i] = 0.0;
   #pragma unroll 1
@@ -259,17 +271,18 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
   blk_sum_vec(c, v, 45);
   if (c.wid == 0) {   // warp 0: parallel-order Jacobi on the 9x9 normal matrix
     WarpScratch* ws = &c.sc->ws[0];
-    warp_min_eigvec9_packed(ws, c.sc->vec_out, c.lane, DG_DEVICE_PASS ? 32 : 1);
+    { DG_PROF_BEGIN(29); warp_min_eigvec9_packed(ws, c.sc->vec_out, c.lane, DG_DEVICE_PASS ? 32 : 1); DG_PROF_END(29); }
     if (c.lane == 0) {
       double q[9];
       for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
-      enforce_rank2(q);
+      { DG_PROF_BEGIN(24); enforce_rank2(q); DG_PROF_END(24); }
       denorm_F(q, A1, A2);
       for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
     }
   }
   bc_fetch(c, f, 9);
   DG_PROF_END(8);
+  DG_PROF_END(40);
 }
 
 }  // namespace dg

@@ -169,8 +169,82 @@ DG_HDN void svd3_onesided(const double* A, double* Gout, double* Vout, double* s
   for (int i = 0; i < 9; ++i) { Gout[i] = G[i]; Vout[i] = V[i]; }
 }
 
-// Rank-2 projection F <- U diag(s0,s1,0) V^T == F - (F v_min) v_min^T   (reference: singulF)
+// 2^-e for the binary exponent e of a positive normal double (exact power of two; 0 when t is not usable).
+DG_HD double pow2_inv_exponent(double t) {
+  if (!(t > 1e-290) || !(t < 1e290)) return 0.0;
+#if DG_DEVICE_PASS
+  const int hi = __double2hiint(t);
+  return __hiloint2double((2046 - ((hi >> 20) & 0x7ff)) << 20, 0);
+#else
+  int e;
+  frexp(t, &e);
+  return ldexp(1.0, 1 - e);
+#endif
+}
+
+// Right singular vector v of the SMALLEST singular value of the 3x3 row-major F, without an SVD:
+// the cofactor matrix C of F = U S V^T is U diag(s1 s2, s0 s2, s0 s1) V^T (up to sign), so v is the dominant
+// eigenvector of K = C^T C, whose eigenvalue ratio is (s2/s1)^2.  Seven squarings of K (power 128) leave a
+// numerically rank-one matrix whenever s2/s1 < ~0.85; its largest column is v.  Working on the cofactors
+// instead of F^T F keeps the accuracy at eps * s1/(s1 - s2) even for badly scaled F (un-normalised 8-point
+// fits).  Returns false (caller falls back to the Jacobi SVD) when the residual test fails.
+DG_HD bool smallest_right_sv3_fast(const double* F, double* v) {
+  double C[9];
+  C[0] = F[4] * F[8] - F[5] * F[7]; C[1] = F[5] * F[6] - F[3] * F[8]; C[2] = F[3] * F[7] - F[4] * F[6];
+  C[3] = F[2] * F[7] - F[1] * F[8]; C[4] = F[0] * F[8] - F[2] * F[6]; C[5] = F[1] * F[6] - F[0] * F[7];
+  C[6] = F[1] * F[5] - F[2] * F[4]; C[7] = F[2] * F[3] - F[0] * F[5]; C[8] = F[0] * F[4] - F[1] * F[3];
+  // K = C^T C, symmetric: k00 k01 k02 k11 k12 k22
+  double k00 = C[0] * C[0] + C[3] * C[3] + C[6] * C[6];
+  double k01 = C[0] * C[1] + C[3] * C[4] + C[6] * C[7];
+  double k02 = C[0] * C[2] + C[3] * C[5] + C[6] * C[8];
+  double k11 = C[1] * C[1] + C[4] * C[4] + C[7] * C[7];
+  double k12 = C[1] * C[2] + C[4] * C[5] + C[7] * C[8];
+  double k22 = C[2] * C[2] + C[5] * C[5] + C[8] * C[8];
+  const double sc = pow2_inv_exponent(k00 + k11 + k22);
+  if (sc == 0.0) return false;
+  k00 *= sc; k01 *= sc; k02 *= sc; k11 *= sc; k12 *= sc; k22 *= sc;   // trace in [1,2): 7 squarings stay in range
+  double m00 = k00, m01 = k01, m02 = k02, m11 = k11, m12 = k12, m22 = k22;
+#pragma unroll
+  for (int it = 0; it < 7; ++it) {
+    const double n00 = m00 * m00 + m01 * m01 + m02 * m02;
+    const double n01 = m00 * m01 + m01 * m11 + m02 * m12;
+    const double n02 = m00 * m02 + m01 * m12 + m02 * m22;
+    const double n11 = m01 * m01 + m11 * m11 + m12 * m12;
+    const double n12 = m01 * m02 + m11 * m12 + m12 * m22;
+    const double n22 = m02 * m02 + m12 * m12 + m22 * m22;
+    m00 = n00; m01 = n01; m02 = n02; m11 = n11; m12 = n12; m22 = n22;
+  }
+  double x, y, z;
+  if (m00 >= m11 && m00 >= m22) { x = m00; y = m01; z = m02; }
+  else if (m11 >= m22)          { x = m01; y = m11; z = m12; }
+  else                          { x = m02; y = m12; z = m22; }
+  const double n2 = x * x + y * y + z * z;
+  if (!(n2 > 0.0) || !(n2 < 1e300)) return false;
+  const double r = DG_RSQRT(n2);
+  x *= r; y *= r; z *= r;
+  // residual against the (scaled) K itself
+  const double w0 = k00 * x + k01 * y + k02 * z;
+  const double w1 = k01 * x + k11 * y + k12 * z;
+  const double w2 = k02 * x + k12 * y + k22 * z;
+  const double mu = w0 * x + w1 * y + w2 * z;
+  const double r0 = w0 - mu * x, r1 = w1 - mu * y, r2 = w2 - mu * z;
+  if (!(r0 * r0 + r1 * r1 + r2 * r2 <= 1e-29 * (mu * mu))) return false;
+  v[0] = x; v[1] = y; v[2] = z;
+  return true;
+}
+
+// Rank-2 projection F <- U diag(s0,s1,0) V^T == F - (F v_min) v_min^T   (reference: singulF, Ftools.c:330-347)
 DG_HDN void enforce_rank2(double* F) {
+  double v[3];
+  if (smallest_right_sv3_fast(F, v)) {
+    const double g0 = F[0] * v[0] + F[1] * v[1] + F[2] * v[2];
+    const double g1 = F[3] * v[0] + F[4] * v[1] + F[5] * v[2];
+    const double g2 = F[6] * v[0] + F[7] * v[1] + F[8] * v[2];
+    F[0] -= g0 * v[0]; F[1] -= g0 * v[1]; F[2] -= g0 * v[2];
+    F[3] -= g1 * v[0]; F[4] -= g1 * v[1]; F[5] -= g1 * v[2];
+    F[6] -= g2 * v[0]; F[7] -= g2 * v[1]; F[8] -= g2 * v[2];
+    return;
+  }
   double G[9], V[9], sv[3];
   svd3_onesided(F, G, V, sv);
   int m = 0;

@@ -1,3 +1,5 @@
+#include <stdio.h>
+#include <stdlib.h>
 // hostemu.cpp -- TEST HELPER ONLY.  Compiles the engine headers with plain g++ as a one-thread CTA
 // (tid=0, nt=1, barriers are no-ops) so the ordered-replay control flow can be checked against the
 // reference on a machine without a GPU.  Never loaded by the pydegensac_b200 package.

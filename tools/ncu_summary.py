@@ -5,7 +5,7 @@ import bisect, csv, io, re, subprocess, sys, os
 
 rep, out = sys.argv[1], sys.argv[2]
 npairs = int(sys.argv[3]) if len(sys.argv) > 3 else None
-lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pydegensac_b200", "libdegensac_b200.so")
+lib = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pydegensac_b200", "libdegensac_b200.so")
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -61,6 +61,9 @@ try:
     data = srows[2:]
     base = int(data[0][ia], 16)
     starts = [s[0] for s in syms]
+    reasons = ["stall_barrier", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_math", "stall_no_inst", "stall_branch_resolving", "stall_mio", "stall_lg", "stall_dispatch", "stall_not_selected", "stall_selected"]
+    ridx = [h2.index(x) for x in reasons]
+    rs = {}
     agg, smp = {}, {}
     for r in data:
         off = int(r[ia], 16) - base
@@ -70,11 +73,20 @@ try:
             name = syms[k][2]
         agg[name] = agg.get(name, 0) + int(r[ie] or 0)
         smp[name] = smp.get(name, 0) + int(r[isamp] or 0)
+        v = rs.setdefault(name, [0] * len(reasons))
+        for q, ix in enumerate(ridx): v[q] += int(r[ix] or 0)
     tot = sum(agg.values()); ts = max(1, sum(smp.values()))
     lines.append("")
     lines.append("device function                executed warp-instr share   (M per pair)   stall-sample share")
     for k, v in sorted(agg.items(), key=lambda x: -x[1])[:26]:
         lines.append("  %-30s %6.2f %%   %10s   %6.1f %%" % (k, 100.0 * v / tot, ("%.2f" % (v / npairs / 1e6)) if npairs else "-", 100.0 * smp[k] / ts))
+    lines.append("")
+    lines.append("stall samples by reason (%% of the function's samples) and cycles per issued warp-instruction")
+    lines.append("  %-30s %s  cyc/instr" % ("function", " ".join("%8s" % x.replace("stall_", "")[:8] for x in reasons)))
+    for k, v in sorted(agg.items(), key=lambda x: -smp[x[0]])[:26]:
+        t = max(1, sum(rs[k]))
+        sel = max(1, rs[k][reasons.index("stall_selected")])
+        lines.append("  %-30s %s  %8.1f" % (k, " ".join("%8.1f" % (100.0 * x / t) for x in rs[k]), t / sel))
 except Exception as ex:  # pragma: no cover
     lines.append("(per-function breakdown unavailable: %r)" % (ex,))
 open(out, "w").write("\n".join(lines) + "\n")
