@@ -16,12 +16,16 @@ constexpr int kVecRed = 48;        // widest vector reduction (45 covariance ent
 struct BlockScratch {
   double red_d[kMaxWarps];
   int red_i[kMaxWarps];
-  double vec[kMaxWarps * kVecRed];
   double vec_out[kVecRed];
   double bc[32];                   // broadcast area for small results (models, scalars)
   int bci[16];
   int counter[4];                  // atomic counters of the hypothesis wave
-  WarpScratch ws[5];               // per-warp tiles for the cooperative 9x9 solves (5 = checksample triplets)
+  WarpScratch ws[1];               // warp 0's tile for the cooperative 9x9 / 8x9 solves
+  union {                          // never live at the same time:
+    WarpScratch wsx[4];            //   tiles of warps 1..4 (the five checksample triplets run side by side)
+    double vec[kMaxWarps * kVecRed];   // per-warp slots of the wide block reductions
+  };
+  DG_ENG WarpScratch* warp_tile(int wid) { return wid == 0 ? &ws[0] : &wsx[wid - 1]; }
 };
 
 struct Tile32;

@@ -184,11 +184,11 @@ DG_ENGN bool blk_checksample(const Ctx& c, const double* F, const double* u7, do
     #pragma unroll 1
     for (int t = c.wid; t < 5; t += par) {
       double Ht[9];
-      const bool ok = warp_checksample_triplet(&c.sc->ws[c.wid], F, u7, t, th, Ht, c.lane, W);
+      const bool ok = warp_checksample_triplet(c.sc->warp_tile(c.wid), F, u7, t, th, Ht, c.lane, W);
       if (c.lane == 0) {
         c.sc->bci[t] = ok ? 1 : 0;
         if (t < 3) { for (int i = 0; i < 9; ++i) c.sc->bc[9 * t + i] = Ht[i]; }
-        else { for (int i = 0; i < 9; ++i) c.sc->vec[9 * (t - 3) + i] = Ht[i]; }
+        else { for (int i = 0; i < 9; ++i) c.sc->vec_out[9 * (t - 3) + i] = Ht[i]; }
       }
     }
   }
@@ -198,7 +198,7 @@ DG_ENGN bool blk_checksample(const Ctx& c, const double* F, const double* u7, do
     if (c.sc->bci[t]) { win = t; break; }
   // the reference leaves the LAST tested triplet's H in the buffer when none succeeds; it is unused then
   const int src = win < 0 ? 4 : win;
-  for (int i = 0; i < 9; ++i) H[i] = (src < 3) ? c.sc->bc[9 * src + i] : c.sc->vec[9 * (src - 3) + i];
+  for (int i = 0; i < 9; ++i) H[i] = (src < 3) ? c.sc->bc[9 * src + i] : c.sc->vec_out[9 * (src - 3) + i];
   DG_SYNC();
   return win >= 0;
 }
@@ -361,6 +361,51 @@ DG_ENGN unsigned blk_u2Fit(const Ctx& c, Workspace& W, double* F, unsigned char*
   return (unsigned)no_i;
 }
 
+#if DG_DEVICE_PASS
+// Positions 0..S-1 of an identity permutation after the swaps `pos <-> idx[pos]` (pos = 0..S-1), replayed on a
+// register log of writes (later entries override earlier ones).  idx[pos] comes from lane base+pos.
+template <int S>
+__device__ __forceinline__ void identity_swaps(int drawmod, int base, int (&out)[S]) {
+  const unsigned full = 0xffffffffu;
+  int tp[2 * S], tv[2 * S];
+#pragma unroll
+  for (int pos = 0; pos < S; ++pos) {
+    const int idx = __shfl_sync(full, drawmod, base + pos);
+    int vp = pos, vi = idx;
+#pragma unroll
+    for (int t = 0; t < 2 * pos; ++t) {
+      if (tp[t] == pos) vp = tv[t];
+      if (tp[t] == idx) vi = tv[t];
+    }
+    tp[2 * pos] = pos;     tv[2 * pos] = vi;
+    tp[2 * pos + 1] = idx; tv[2 * pos + 1] = vp;
+  }
+#pragma unroll
+  for (int pos = 0; pos < S; ++pos) {
+    int v = pos;
+#pragma unroll
+    for (int t = 0; t < 2 * S; ++t) if (tp[t] == pos) v = tv[t];
+    out[pos] = v;
+  }
+}
+// dual_sample on one warp: the ten draws are generated by ten lanes at once, the swaps replayed in registers.
+__device__ __noinline__ void warp_dual_sample(const int* uH, int nH, const int* uO, int nO, int* usam, uint64_t seed,
+                                              uint32_t k, uint32_t j0, int lane) {
+  int dm = 0;
+  if (lane < 10) dm = (int)(value31(seed, k, j0 + (uint32_t)lane) % (uint32_t)(lane < 6 ? nH : nO));
+  int ph[6], po[4];
+  identity_swaps<6>(dm, 0, ph);
+  identity_swaps<4>(dm, 6, po);
+  int mine = 0;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) if (lane == q) mine = ph[q];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) if (lane == 6 + q) mine = po[q];
+  if (lane < 6) usam[lane] = uH[mine];
+  else if (lane < 10) usam[lane] = uO[mine];
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // LO of F from plane + off-plane correspondences (reference innerFH + dual_sample, DegUtils.c:488-632).
 // uH list (plane inliers, nH), uO list (off-plane support, nO), 15 reps of 6 + 4 points.
@@ -381,6 +426,9 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
     // dual_sample: fresh identity permutations, `pos <-> rand()%len` swaps (DegUtils.c:596-632)
     DG_PROF_BEGIN(36);
     DG_SYNC();
+#if DG_DEVICE_PASS
+    if (c.wid == 0) warp_dual_sample(uH, nH, uO, nO, usam, cur.seed, cur.k, cur.j, c.lane);
+#else
     if (c.tid == 0) {
       DrawCursor t = cur;
       int tp[12], tv[12], nt;
@@ -412,6 +460,7 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
         }
       }
     }
+#endif
     cur.j += 10;
     DG_SYNC();
     DG_PROF_END(36);
@@ -503,25 +552,40 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
   const int WAVE = c.nw * 8;
   int* pairs = W.itmp[2] + 16;   // WAVE x 2 sampled positions
   int* counts = W.itmp[2] + 16 + 2 * 128;
+  int* idxs = reinterpret_cast<int*>(c.sc->vec);   // 2 x 128 swap partners of the current wave (block scratch is idle here)
   unsigned no_sam = 1;
   while (no_sam < 2 * max_sam) {
     int nw = (int)(2 * max_sam - no_sam);
     if (nw > WAVE) nw = WAVE;
     if (nw > 128) nw = 128;
-    // thread 0 advances the persistent permutation speculatively for nw iterations
+    // All threads: the 2*nw draws of the speculative iterations (swap partners) go to shared memory, and the
+    // entries of the persistent permutation they address are pulled towards L1.  Thread 0 then replays the swaps
+    // in order with ptr[0], ptr[1] held in registers.
     DG_PROF_BEGIN(32);
     DG_SYNC();
+    #pragma unroll 1
+    for (int q = c.tid; q < 2 * nw; q += c.nt) {
+      const int pos = q & 1;
+      const int idx = pos + 1 + (int)(value31(cur.seed, cur.k, cur.j + (uint32_t)q) % (uint32_t)(nN - pos - 1));
+      idxs[q] = idx;
+#if DG_DEVICE_PASS
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr + idx));
+#endif
+    }
+    DG_SYNC();
     if (c.tid == 0) {
-      DrawCursor t = cur;
+      int p0 = ptr[0], p1 = ptr[1];
       #pragma unroll 1
       for (int s = 0; s < nw; ++s) {
-        for (int pos = 0; pos < 2; ++pos) {
-          const int idx = pos + 1 + (int)(next_draw(t) % (uint32_t)(nN - pos - 1));
-          const int a = ptr[pos]; ptr[pos] = ptr[idx]; ptr[idx] = a;
-        }
-        pairs[2 * s] = ptr[0];
-        pairs[2 * s + 1] = ptr[1];
+        const int i0 = idxs[2 * s], i1 = idxs[2 * s + 1];
+        int v;
+        if (i0 == 1) { v = p1; p1 = p0; } else { v = ptr[i0]; ptr[i0] = p0; }
+        p0 = v;
+        v = ptr[i1]; ptr[i1] = p1; p1 = v;
+        pairs[2 * s] = p0;
+        pairs[2 * s + 1] = p1;
       }
+      ptr[0] = p0; ptr[1] = p1;
     }
     DG_SYNC();
     // one warp per two-point hypothesis: support count over the off-plane correspondences
@@ -557,12 +621,6 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
     // rewind the permutation to the state right after iteration `ev` (undo swaps ev+1..nw-1 in reverse)
     DG_SYNC();
     if (c.tid == 0) {
-      DrawCursor t = cur;
-      t.j += 2u * (uint32_t)(ev + 1);
-      int idxs[2 * 128];
-      #pragma unroll 1
-      for (int s = ev + 1; s < nw; ++s)
-        for (int pos = 0; pos < 2; ++pos) idxs[2 * s + pos] = pos + 1 + (int)(next_draw(t) % (uint32_t)(nN - pos - 1));
       #pragma unroll 1
       for (int s = nw - 1; s > ev; --s)
         #pragma unroll 1

@@ -52,8 +52,8 @@ int cfg_threads() {
   return v;
 }
 int cfg_smem_tile() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DGB200_SMEM_TILE"); v = e ? atoi(e) : 0; }
+  static int v = -2;
+  if (v < -1) { const char* e = getenv("DGB200_SMEM_TILE"); v = e ? atoi(e) : 0; }   // measured on B200: the L1 capacity the tile takes away costs more than it saves
   return v;
 }
 
@@ -209,20 +209,30 @@ int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, doub
   a.model_out = d_model; a.mask_out = d_mask; a.stats_out = d_stats;
   a.chunk = kChunk;
   const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128);
-  const size_t tile = dg::align_up(sizeof(double) * (size_t)n, 128) * 4;
-  size_t smem = sc_bytes + tile;
-  a.pts_in_smem = cfg_smem_tile() ? 1 : 0;
-  if (!a.pts_in_smem || smem > g_c.smem_optin) { smem = sc_bytes; a.pts_in_smem = 0; }
-  a.tile32_in_smem = 0;
-  if (KIND == 0 && 16 * (size_t)n <= 65536 && smem + dg::align_up(16 * (size_t)n, 128) <= g_c.smem_optin) {
-    a.tile32_in_smem = 1;
-    smem += dg::align_up(16 * (size_t)n, 128);
-  }
+  const size_t tile = dg::align_up(sizeof(double) * (size_t)n, 128) * 4;       // FP64 SoA of the pair
+  const size_t tile32 = (KIND == 0 && 16 * (size_t)n <= 65536) ? dg::align_up(16 * (size_t)n, 128) : 0;   // FP32 filter tile
   const int kThreads = cfg_threads();
   auto kern = ransac_pairs_kernel<KIND>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // Shared-memory plan: block scratch always; the FP32 filter tile when it fits.  The FP64 correspondences stay in
+  // global memory (L1/L2-resident): DGB200_SMEM_TILE=1 moves them to shared memory too, which measured 12 % slower
+  // at N = 2000 (10.2k vs 11.6k pairs/s) because the residual rows and lists then lose their L1 capacity.
+  size_t smem = sc_bytes;
+  a.pts_in_smem = 0;
+  a.tile32_in_smem = 0;
+  if (tile32 && smem + tile32 <= g_c.smem_optin) { a.tile32_in_smem = 1; smem += tile32; }
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  const int want_tile = cfg_smem_tile();
+  if (want_tile != 0 && smem + tile <= g_c.smem_optin) {
+    const size_t smem_full = smem + tile;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem_full));
+    if (occ >= 2 || (want_tile > 0 && occ >= 1)) { a.pts_in_smem = 1; smem = smem_full; per_sm = occ; }
+  }
+  if (!a.pts_in_smem) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  }
   if (per_sm < 1) return fail(DGB200_E_CUDA, "kernel does not fit on an SM");
   if (const char* e = getenv("DGB200_CTAS_PER_SM")) { const int cap = atoi(e); if (cap >= 1 && cap < per_sm) per_sm = cap; }
   int grid = g_c.sm_count * per_sm;     // persistent CTAs: a whole number of CTAs per SM

@@ -36,35 +36,6 @@ static long g_filter_checked = 0, g_filter_violations = 0;
 static double g_filter_maxslack = 0.0;
 #endif
 
-// ------------------------------------------------------------------------------ LO hash table
-// The reference de-duplicates LO inlier sets with SuperFastHash + a 64-bucket chained table
-// (hash.c:49-96, exp_ranF.c:675-686).  Only "(hash,len) seen under this iterID / another iterID /
-// never" matters, so a flat list is equivalent.  Returns true when the refinement must abort.
-DG_ENGN bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
-  DG_PROF_BEGIN(4);
-  DG_SYNC();
-  if (c.tid == 0) {
-    const uint32_t h = superfasthash_i32(list, n);
-    int same = 0, other = 0;
-    #pragma unroll 1
-    for (int i = 0; i < ht.n; ++i) {
-      if (W.hhash[i] == h && W.hlen[i] == n) {
-        if (W.hid[i] == iterID) same = 1; else other = 1;
-      }
-    }
-    int verdict = 0;  // 0: insert, 1: already ours, 2: abort
-    if (same) verdict = 1; else if (other) verdict = 2;
-    if (verdict == 0 && ht.n < W.hcap) { W.hhash[ht.n] = h; W.hlen[ht.n] = n; W.hid[ht.n] = iterID; }
-    c.sc->bci[0] = verdict;
-  }
-  DG_SYNC();
-  const int verdict = c.sc->bci[0];
-  DG_SYNC();
-  if (verdict == 0 && ht.n < W.hcap) ++ht.n;
-  DG_PROF_END(4);
-  return verdict == 2;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Iterated re-weighted LSQ with shrinking threshold (reference exp_iterFcustom, exp_ranF.c:621-743).
 // e[] are the physical ids behind the reference's errs[] pointers; e[4] holds the residual row of the

@@ -44,25 +44,9 @@ DG_ENGN unsigned blk_sym_count_H(const Ctx& c, const double* h, const int* list,
   return (unsigned)blk_sum_i(c, cnt);
 }
 
-// hash de-duplication shared with the F engine's table layout
-DG_ENGN bool hash_seen_elsewhere_h(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
-  DG_SYNC();
-  if (c.tid == 0) {
-    const uint32_t h = superfasthash_i32(list, n);
-    int same = 0, other = 0;
-    #pragma unroll 1
-    for (int i = 0; i < ht.n; ++i)
-      if (W.hhash[i] == h && W.hlen[i] == n) { if (W.hid[i] == iterID) same = 1; else other = 1; }
-    int verdict = 0;
-    if (same) verdict = 1; else if (other) verdict = 2;
-    if (verdict == 0 && ht.n < W.hcap) { W.hhash[ht.n] = h; W.hlen[ht.n] = n; W.hid[ht.n] = iterID; }
-    c.sc->bci[0] = verdict;
-  }
-  DG_SYNC();
-  const int verdict = c.sc->bci[0];
-  DG_SYNC();
-  if (verdict == 0 && ht.n < W.hcap) ++ht.n;
-  return verdict == 2;
+// hash de-duplication: same table and routine as the F engine (ffit.h)
+DG_ENG inline bool hash_seen_elsewhere_h(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
+  return hash_seen_elsewhere(c, W, ht, list, n, iterID);
 }
 
 // Iterated LSQ with shrinking threshold (reference exp_iterHcustom, exp_ranH.c:291-411; inlLimit = 1e6

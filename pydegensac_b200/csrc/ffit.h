@@ -76,11 +76,59 @@ DG_ENGN unsigned blk_sym_count_F(const Ctx& c, const double* F, const int* list,
   return (unsigned)blk_sum_i(c, cnt);
 }
 
+#if DG_DEVICE_PASS
+// Warp flavour of randsubset (siz <= MAXS): lane i draws value i, computes its slot and prefetches both entries of
+// its swap; the swaps are then replayed on a register-resident log of (position, value) writes -- later entries
+// override earlier ones, as in minimal_sample -- by every lane redundantly, and each lane stores the final value of
+// the two positions it touched.  Same result as the sequential loop below, without eight dependent round trips
+// to the list (which lives in L2: it was written by other warps a moment ago).
+template <int MAXS>
+__device__ __noinline__ void warp_randsubset(int* list, int max_sz, int siz, uint64_t seed, uint32_t k, uint32_t j0, int lane) {
+  const unsigned full = 0xffffffffu;
+  int s = 0, top = 0, vs = 0, vt = 0;
+  if (lane < siz) {
+    s = (int)(value31(seed, k, j0 + (uint32_t)lane) % (uint32_t)(max_sz - lane));
+    top = max_sz - lane - 1;
+    vs = list[s];
+    vt = list[top];
+  }
+  int tp[2 * MAXS], tv[2 * MAXS];
+#pragma unroll
+  for (int q = 0; q < MAXS; ++q) {
+    const int sq = __shfl_sync(full, s, q), tq = __shfl_sync(full, top, q);
+    int a = __shfl_sync(full, vs, q), b = __shfl_sync(full, vt, q);
+#pragma unroll
+    for (int t = 0; t < 2 * q; ++t) {
+      if (tp[t] == sq) a = tv[t];
+      if (tp[t] == tq) b = tv[t];
+    }
+    const bool live = q < siz;
+    tp[2 * q] = live ? sq : -1;     tv[2 * q] = b;        // list[s]   <- value that sat at the top slot
+    tp[2 * q + 1] = live ? tq : -1; tv[2 * q + 1] = a;    // list[top] <- the drawn value
+  }
+  if (lane < siz) {
+    int fs = vs, ft = vt;
+#pragma unroll
+    for (int t = 0; t < 2 * MAXS; ++t) {
+      if (tp[t] == s) fs = tv[t];
+      if (tp[t] == top) ft = tv[t];
+    }
+    list[s] = fs;
+    list[top] = ft;
+  }
+}
+#endif
+
 // Partial Fisher-Yates permutation of list[0..max_sz) drawing `siz` slots; the subset is the last
-// `siz` entries (reference randsubset, rtools.c:25-39).  Sequential by nature: thread 0.
+// `siz` entries (reference randsubset, rtools.c:25-39).
 DG_ENGN void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCursor& cur) {
   DG_PROF_BEGIN(23);
   DG_SYNC();
+#if DG_DEVICE_PASS
+  if (siz <= 14) {
+    if (c.wid == 0) warp_randsubset<14>(list, max_sz, siz, cur.seed, cur.k, cur.j, c.lane);
+  } else
+#endif
   if (c.tid == 0) {
     DrawCursor t = cur;
     #pragma unroll 1
@@ -250,25 +298,58 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
   if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
   A1[1] *= -A1[0]; A1[2] *= -A1[0];
   A2[1] *= -A2[0]; A2[2] *= -A2[0];
-  // normal matrix of the normalised rows (reference lin_fmN + cov_mat, Ftools.c:300-328, utools.c:170-184)
-  #pragma unroll 1
-  for (int i = 0; i < 45; ++i) v[i] = 0.0;
-  #pragma unroll 1
-  for (int j = c.tid; j < len; j += c.nt) {
-    const int p = idx[j];
-    double a[3], b[3], row[9];
-    a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
-    b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
-    for (int k = 0; k < 3; ++k)
-      for (int l = 0; l < 3; ++l) row[3 * k + l] = a[l] * b[k];
-    const double ww = w ? w[p] : 1.0;
-    if (w) for (int k = 0; k < 9; ++k) row[k] *= ww;
-    int t = 0;
-    for (int i = 0; i < 9; ++i)
+  // normal matrix of the normalised rows (reference lin_fmN + cov_mat, Ftools.c:300-328, utools.c:170-184).
+  // Each thread keeps the rows of up to three correspondences in registers; every one of the 45 entries is formed
+  // from them and reduced across the warp at once (no per-thread 45-entry accumulator, hence no local memory),
+  // lane 0 adds the warp's partial sum to its slot in shared memory; the slots are combined after the barrier.
+  {
+    double* slot = c.sc->vec + c.wid * kVecRed;
+    DG_SYNC();
+    #pragma unroll 1
+    for (int t = c.lane; t < 45; t += (DG_DEVICE_PASS ? 32 : 1)) slot[t] = 0.0;
+    DG_WSYNC();
+    #pragma unroll 1
+    for (int base = 0; base < len; base += 3 * c.nt) {
+      double r[3][9];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int j = base + q * c.nt + c.tid;
+        if (j < len) {
+          const int p = idx[j];
+          const double a0 = c.x1[p] * A1[0] + A1[1], a1 = c.y1[p] * A1[0] + A1[2];
+          const double b0 = c.x2[p] * A2[0] + A2[1], b1 = c.y2[p] * A2[0] + A2[2];
+          r[q][0] = a0 * b0; r[q][1] = a1 * b0; r[q][2] = b0;
+          r[q][3] = a0 * b1; r[q][4] = a1 * b1; r[q][5] = b1;
+          r[q][6] = a0;      r[q][7] = a1;      r[q][8] = 1.0;
+          if (w) {
+            const double ww = w[p];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) r[q][k] *= ww;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) r[q][k] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int jj = 0; jj <= i; ++jj) {
+          double sum = r[0][i] * r[0][jj] + r[1][i] * r[1][jj] + r[2][i] * r[2][jj];
+          sum = warp_sum(sum);
+          if (c.lane == 0) slot[i * (i + 1) / 2 + jj] += sum;
+        }
+    }
+    DG_SYNC();
+    #pragma unroll 1
+    for (int t = c.tid; t < 45; t += c.nt) {
+      double sum = 0.0;
       #pragma unroll 1
-      for (int jj = 0; jj <= i; ++jj) v[t++] += row[i] * row[jj];
+      for (int wv = 0; wv < c.nw; ++wv) sum += c.sc->vec[wv * kVecRed + t];
+      c.sc->vec_out[t] = sum;
+    }
+    DG_SYNC();
   }
-  blk_sum_vec(c, v, 45);
   if (c.wid == 0) {   // warp 0: parallel-order Jacobi on the 9x9 normal matrix
     WarpScratch* ws = &c.sc->ws[0];
     { DG_PROF_BEGIN(29); warp_min_eigvec9_packed(ws, c.sc->vec_out, c.lane, DG_DEVICE_PASS ? 32 : 1); DG_PROF_END(29); }
@@ -283,6 +364,78 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
   bc_fetch(c, f, 9);
   DG_PROF_END(8);
   DG_PROF_END(40);
+}
+
+// ------------------------------------------------------------------------------ LO hash table
+// The reference de-duplicates LO inlier sets with SuperFastHash + a 64-bucket chained table
+// (hash.c:49-96, exp_ranF.c:675-686).  Only "(hash,len) seen under this iterID / another iterID /
+// never" matters, so a flat list is equivalent.  Returns true when the refinement must abort.
+DG_ENGN bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
+  DG_PROF_BEGIN(4);
+  DG_SYNC();
+#if DG_DEVICE_PASS
+  // Warp 0: the list is fetched 32 words at a time (coalesced, next block in flight while the current one is
+  // hashed), every lane runs the same serial SuperFastHash chain on words handed round by shuffles, and the table
+  // scan is spread over the lanes.  The chain itself cannot be parallelised; this removes the memory latency from it.
+  if (c.wid == 0) {
+    const unsigned full = 0xffffffffu;
+    uint32_t h = 0u;
+    if (n > 0) {
+      h = sfh_init(n);
+      uint32_t v = (c.lane < n) ? (uint32_t)list[c.lane] : 0u;
+      #pragma unroll 1
+      for (int base = 0; base < n; base += 32) {
+        const int nxt = base + 32 + c.lane;
+        const uint32_t vn = (nxt < n) ? (uint32_t)list[nxt] : 0u;
+        if (n - base >= 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h = sfh_word(h, __shfl_sync(full, v, j));
+        } else {
+          #pragma unroll 1
+          for (int j = 0; j < n - base; ++j) h = sfh_word(h, __shfl_sync(full, v, j));
+        }
+        v = vn;
+      }
+      h = sfh_final(h);
+    }
+    bool same = false, other = false;
+    #pragma unroll 1
+    for (int i = c.lane; i < ht.n; i += 32) {
+      if (W.hhash[i] == h && W.hlen[i] == n) {
+        if (W.hid[i] == iterID) same = true; else other = true;
+      }
+    }
+    same = __any_sync(full, same);
+    other = __any_sync(full, other);
+    int verdict = 0;  // 0: insert, 1: already ours, 2: abort
+    if (same) verdict = 1; else if (other) verdict = 2;
+    if (c.lane == 0) {
+      if (verdict == 0 && ht.n < W.hcap) { W.hhash[ht.n] = h; W.hlen[ht.n] = n; W.hid[ht.n] = iterID; }
+      c.sc->bci[0] = verdict;
+    }
+  }
+#else
+  if (c.tid == 0) {
+    const uint32_t h = superfasthash_i32(list, n);
+    int same = 0, other = 0;
+    #pragma unroll 1
+    for (int i = 0; i < ht.n; ++i) {
+      if (W.hhash[i] == h && W.hlen[i] == n) {
+        if (W.hid[i] == iterID) same = 1; else other = 1;
+      }
+    }
+    int verdict = 0;  // 0: insert, 1: already ours, 2: abort
+    if (same) verdict = 1; else if (other) verdict = 2;
+    if (verdict == 0 && ht.n < W.hcap) { W.hhash[ht.n] = h; W.hlen[ht.n] = n; W.hid[ht.n] = iterID; }
+    c.sc->bci[0] = verdict;
+  }
+#endif
+  DG_SYNC();
+  const int verdict = c.sc->bci[0];
+  DG_SYNC();
+  if (verdict == 0 && ht.n < W.hcap) ++ht.n;
+  DG_PROF_END(4);
+  return verdict == 2;
 }
 
 }  // namespace dg
