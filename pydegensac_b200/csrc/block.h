@@ -152,6 +152,13 @@ DG_ENG inline void blk_scan_sum(const Ctx& c, int cnt, double J, int* off, int* 
 // J = sum truncQuad(err, th), list = {i : err[i] <= th}.  Threads own contiguous index segments so the list comes
 // out ordered after one block scan; up to 8 residuals per thread stay in registers between counting and writing
 // (one global read of the row, two barriers).
+#if DG_DEVICE_PASS
+// residual rows are streamed (written once, read once or twice): keep them out of L1 so the correspondences stay there
+DG_ENG inline double ld_row(const double* p) { return __ldcg(p); }
+#else
+inline double ld_row(const double* p) { return *p; }
+#endif
+
 DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list) {
   DG_PROF_BEGIN(21);
   DG_PROF_COUNT(22, 1);
@@ -171,7 +178,7 @@ DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int i = beg + j;
-      e[j] = (i < end) ? err[i] : INFINITY;
+      e[j] = (i < end) ? ld_row(err + i) : INFINITY;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -185,14 +192,14 @@ DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list)
   } else {
     #pragma unroll 1
     for (int i = beg; i < end; ++i) {
-      const double e = err[i];
+      const double e = ld_row(err + i);
       if (th != 0 && !(e >= wq)) J += 1 - e * winv;
       if (e <= th) ++cnt;
     }
     blk_scan_sum(c, cnt, J, &off, &total, &Jtot);
     #pragma unroll 1
     for (int i = beg; i < end; ++i)
-      if (err[i] <= th) list[off++] = i;
+      if (ld_row(err + i) <= th) list[off++] = i;
   }
   s.J = Jtot;
   s.I = (unsigned)total;

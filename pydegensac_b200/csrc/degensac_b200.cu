@@ -34,7 +34,13 @@ namespace {
 #define DG_LB_BLOCKS 2
 #endif
 constexpr int kMaxThreads = DG_LB_THREADS;
-constexpr int kChunk = 512;
+constexpr int kChunkDefault = 512;
+int cfg_chunk() {   // iterations hypothesised per wave (DGB200_CHUNK, multiple of 128)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DGB200_CHUNK"); v = e ? atoi(e) : kChunkDefault; if (v < 128) v = 128; if (v > 4096) v = 4096; v = (v / 128) * 128; }
+  return v;
+}
+#define kChunk cfg_chunk()
 
 // CTA shape.  256 threads x 2 CTAs per SM measured fastest on B200 (profiles/README.md): the waves and the O(N)
 // passes of the replay want the 8 warps, while more, smaller CTAs per SM lose to instruction-cache misses (each

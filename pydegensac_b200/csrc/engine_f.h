@@ -53,8 +53,7 @@ DG_ENGN Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int* e, in
   if (8 >= S.I) {
     blk_fit_F(c, inl, (int)S.I, nullptr, f);
   } else {
-    blk_randsubset(c, inl, (int)S.I, 8, cur);
-    blk_fit_F(c, inl + S.I - 8, 8, nullptr, f);
+    blk_sample8_fit_F(c, inl, (int)S.I, nullptr, cur, f);
   }
   #pragma unroll 1
   for (int it = 0; it < kIlsqIters; ++it) {
@@ -73,8 +72,7 @@ DG_ENGN Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int* e, in
     if (8 >= Ss.I) {
       blk_fit_F(c, inl, (int)Ss.I, W.w, f);
     } else {
-      blk_randsubset(c, inl, (int)Ss.I, 8, cur);
-      blk_fit_F(c, inl + Ss.I - 8, 8, W.w, f);
+      blk_sample8_fit_F(c, inl, (int)Ss.I, W.w, cur, f);
     }
     ths -= dth;
   }

@@ -83,7 +83,8 @@ DG_ENGN unsigned blk_sym_count_F(const Ctx& c, const double* F, const int* list,
 // the two positions it touched.  Same result as the sequential loop below, without eight dependent round trips
 // to the list (which lives in L2: it was written by other warps a moment ago).
 template <int MAXS>
-__device__ __noinline__ void warp_randsubset(int* list, int max_sz, int siz, uint64_t seed, uint32_t k, uint32_t j0, int lane) {
+__device__ __forceinline__ void warp_randsubset_core(int* list, int max_sz, int siz, uint64_t seed, uint32_t k, uint32_t j0,
+                                                     int lane, int (&drawn)[MAXS]) {
   const unsigned full = 0xffffffffu;
   int s = 0, top = 0, vs = 0, vt = 0;
   if (lane < siz) {
@@ -105,6 +106,7 @@ __device__ __noinline__ void warp_randsubset(int* list, int max_sz, int siz, uin
     const bool live = q < siz;
     tp[2 * q] = live ? sq : -1;     tv[2 * q] = b;        // list[s]   <- value that sat at the top slot
     tp[2 * q + 1] = live ? tq : -1; tv[2 * q + 1] = a;    // list[top] <- the drawn value
+    drawn[q] = a;
   }
   if (lane < siz) {
     int fs = vs, ft = vt;
@@ -117,6 +119,11 @@ __device__ __noinline__ void warp_randsubset(int* list, int max_sz, int siz, uin
     list[top] = ft;
   }
 }
+template <int MAXS>
+__device__ __noinline__ void warp_randsubset(int* list, int max_sz, int siz, uint64_t seed, uint32_t k, uint32_t j0, int lane) {
+  int drawn[MAXS];
+  warp_randsubset_core<MAXS>(list, max_sz, siz, seed, k, j0, lane, drawn);
+}
 #endif
 
 // Partial Fisher-Yates permutation of list[0..max_sz) drawing `siz` slots; the subset is the last
@@ -125,7 +132,9 @@ DG_ENGN void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCu
   DG_PROF_BEGIN(23);
   DG_SYNC();
 #if DG_DEVICE_PASS
-  if (siz <= 14) {
+  if (siz <= 8) {
+    if (c.wid == 0) warp_randsubset<8>(list, max_sz, siz, cur.seed, cur.k, cur.j, c.lane);
+  } else if (siz <= 14) {
     if (c.wid == 0) warp_randsubset<14>(list, max_sz, siz, cur.seed, cur.k, cur.j, c.lane);
   } else
 #endif
@@ -364,6 +373,67 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
   bc_fetch(c, f, 9);
   DG_PROF_END(8);
   DG_PROF_END(40);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Random 8-subset of list[0..max_sz) + F fit on it: exactly blk_randsubset(list, max_sz, 8) followed by
+// blk_fit_F(list + max_sz - 8, 8, w), the step every iteration of the LO's re-weighted LSQ performs (the binding's
+// inlLimit = 0).  Device: one trip through warp 0 -- draws, swap replay, the eight coefficient
+// rows, the (quirky) weighting, Gauss-Jordan and the rank-2 projection all stay in registers; only the permuted
+// list entries and the 9 results touch memory.
+// ---------------------------------------------------------------------------------------------
+DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double* w, DrawCursor& cur, double* f) {
+#if DG_DEVICE_PASS
+  DG_PROF_BEGIN(7);
+  DG_PROF_COUNT(27, 1);
+  DG_SYNC();
+  bool fast = true;
+  if (c.wid == 0) {
+    const unsigned full = 0xffffffffu;
+    int drawn[8];
+    warp_randsubset_core<8>(list, max_sz, 8, cur.seed, cur.k, cur.j, c.lane, drawn);
+    // correspondence of row i is list[max_sz - 8 + i] = the value drawn at step 7 - i
+    const int r = c.lane & 7;
+    int p = drawn[7];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) if (r == q) p = drawn[7 - q];
+    double m[9], n[9];
+    f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], m);
+    if (w) {
+      // the reference scales the row-major 9 x 8 array with stride 9 (Ftools.c:431): entry (coefficient t, row i)
+      // sits at 8 t + i and is multiplied by the weight of correspondence (8 t + i) mod 9 when that is < 8
+      const double wi = w[p];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int src = (8 * t + r) % 9;
+        const double wv = __shfl_sync(full, wi, src & 7);
+        if (src < 8) m[t] *= wv;
+      }
+    }
+    fast = null_8x9_core(m, c.lane, n);
+    if (fast) {
+      enforce_rank2(n);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) if (c.lane == i) c.sc->bc[i] = n[i];
+    }
+    if (c.lane == 0) c.sc->bci[1] = fast ? 1 : 0;
+  }
+  DG_SYNC();
+  fast = c.sc->bci[1] != 0;
+  cur.j += 8u;
+  if (fast) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = c.sc->bc[i];
+    DG_SYNC();
+    DG_PROF_END(7);
+    return;
+  }
+  DG_PROF_END(7);
+  blk_fit_F(c, list + max_sz - 8, 8, w, f);   // rank-deficient sample: Householder route on the (already permuted) list
+#else
+  blk_randsubset(c, list, max_sz, 8, cur);
+  blk_fit_F(c, list + max_sz - 8, 8, w, f);
+#endif
 }
 
 // ------------------------------------------------------------------------------ LO hash table

@@ -273,14 +273,13 @@ __device__ __noinline__ bool warp_smallest_eigvec9_reg(WarpScratch* ws, int lane
 // copies across the warp, so xor-shuffles over 4,2,1 leave every lane with the pivot choice), Gauss-Jordan with
 // partial pivoting by ROLE instead of row swaps: the pivot row of column c stays where it is and is marked used.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ bool warp_null_8x9_reg(WarpScratch* ws, int lane) {
+// Core on registers: lane l holds row (l & 7) in m[0..8]; on success every lane gets the unit null vector n[0..8]
+// (last component positive).
+__device__ __forceinline__ bool null_8x9_core(double (&m)[9], int lane, double (&n)[9]) {
   const unsigned full = 0xffffffffu;
   const int r = lane & 7;
-  double m[9];
-#pragma unroll
-  for (int j = 0; j < 9; ++j) m[j] = ws->A[j * 8 + r];
   bool used = false;
-  int mycol = 8;
+  int whoarr[8];
 #pragma unroll
   for (int col = 0; col < 8; ++col) {
     double mag = used ? -1.0 : fabs(m[col]);
@@ -293,6 +292,7 @@ __device__ __noinline__ bool warp_null_8x9_reg(WarpScratch* ws, int lane) {
       if (m2 > mag || (m2 == mag && w2 < who)) { mag = m2; who = w2; }
     }
     if (!(mag > 0.0) || !(mag < 1e300)) return false;
+    whoarr[col] = who;
     const double p = shfl_d(m[col], who);
     const double inv = 1.0 / p;
     const double f = m[col];
@@ -301,15 +301,28 @@ __device__ __noinline__ bool warp_null_8x9_reg(WarpScratch* ws, int lane) {
       const double pj = shfl_d(m[j], who) * inv;
       if (r == who) m[j] = pj; else m[j] -= f * pj;
     }
-    if (r == who) { used = true; mycol = col; }
+    if (r == who) used = true;
   }
   double n2 = m[8] * m[8];
 #pragma unroll
   for (int o = 4; o > 0; o >>= 1) n2 += __shfl_xor_sync(full, n2, o);
   const double sc = rsqrt(1.0 + n2);
+  const double mine = -m[8] * sc;
+#pragma unroll
+  for (int col = 0; col < 8; ++col) n[col] = shfl_d(mine, whoarr[col]);
+  n[8] = sc;
+  return true;
+}
+
+__device__ __noinline__ bool warp_null_8x9_reg(WarpScratch* ws, int lane) {
+  const int r = lane & 7;
+  double m[9], n[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) m[j] = ws->A[j * 8 + r];
+  if (!null_8x9_core(m, lane, n)) return false;
   __syncwarp();
-  if (lane < 8) ws->cs[mycol] = -m[8] * sc;
-  if (lane == 8) ws->cs[8] = sc;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) if (lane == j) ws->cs[j] = n[j];
   __syncwarp();
   return true;
 }
