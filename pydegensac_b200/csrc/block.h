@@ -155,8 +155,12 @@ DG_ENG inline void blk_scan_sum(const Ctx& c, int cnt, double J, int* off, int* 
 #if DG_DEVICE_PASS
 // residual rows are streamed (written once, read once or twice): keep them out of L1 so the correspondences stay there
 DG_ENG inline double ld_row(const double* p) { return __ldcg(p); }
+DG_ENG inline void st_row(double* p, double v) { __stcg(p, v); }
+DG_ENG inline void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #else
 inline double ld_row(const double* p) { return *p; }
+inline void st_row(double* p, double v) { *p = v; }
+inline void prefetch_l1(const void*) {}
 #endif
 
 DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list) {

@@ -365,7 +365,7 @@ DG_ENGN unsigned blk_u2Fit(const Ctx& c, Workspace& W, double* F, unsigned char*
 // Positions 0..S-1 of an identity permutation after the swaps `pos <-> idx[pos]` (pos = 0..S-1), replayed on a
 // register log of writes (later entries override earlier ones).  idx[pos] comes from lane base+pos.
 template <int S>
-__device__ __forceinline__ void identity_swaps(int drawmod, int base, int (&out)[S]) {
+__device__ __forceinline__ void identity_swaps(int drawmod, int base, int lane, int& mine) {
   const unsigned full = 0xffffffffu;
   int tp[2 * S], tv[2 * S];
 #pragma unroll
@@ -385,7 +385,7 @@ __device__ __forceinline__ void identity_swaps(int drawmod, int base, int (&out)
     int v = pos;
 #pragma unroll
     for (int t = 0; t < 2 * S; ++t) if (tp[t] == pos) v = tv[t];
-    out[pos] = v;
+    if (lane == base + pos) mine = v;    // lane base+pos keeps entry `pos`
   }
 }
 // dual_sample on one warp: the ten draws are generated by ten lanes at once, the swaps replayed in registers.
@@ -393,14 +393,9 @@ __device__ __noinline__ void warp_dual_sample(const int* uH, int nH, const int* 
                                               uint32_t k, uint32_t j0, int lane) {
   int dm = 0;
   if (lane < 10) dm = (int)(value31(seed, k, j0 + (uint32_t)lane) % (uint32_t)(lane < 6 ? nH : nO));
-  int ph[6], po[4];
-  identity_swaps<6>(dm, 0, ph);
-  identity_swaps<4>(dm, 6, po);
   int mine = 0;
-#pragma unroll
-  for (int q = 0; q < 6; ++q) if (lane == q) mine = ph[q];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) if (lane == 6 + q) mine = po[q];
+  identity_swaps<6>(dm, 0, lane, mine);
+  identity_swaps<4>(dm, 6, lane, mine);
   if (lane < 6) usam[lane] = uH[mine];
   else if (lane < 10) usam[lane] = uO[mine];
 }

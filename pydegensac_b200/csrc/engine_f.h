@@ -171,11 +171,55 @@ DG_ENGN bool run_lo_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, 
 // host emulation and the non-generic fallback use -- without its 1.3 KB of local memory per thread.
 // Output per iteration k: W.nsbuf[16*(k-kbeg) + ..] = {-col7[0..6], -col8[0..6], generic?1:0}.
 // ---------------------------------------------------------------------------------------------
+// One pivot column of the pair elimination.  A template (not a loop) so that every index into `a` is a literal
+// in each instantiation: with the seven columns as an unrolled loop the compiler left the whole matrix in local
+// memory (280-byte depot, ~800 local loads/stores per sample).
+template <int COL>
+__device__ __forceinline__ void pairsolve_step(double (&a)[5][7], int h, int lane, bool& generic) {
+  constexpr int owner = (COL < 5) ? 0 : 1;
+  constexpr int lc = COL - 5 * owner;
+  const unsigned full = 0xffffffffu;
+  int best = COL;
+  double mag = 0.0;
+  if (h == owner) {
+    mag = fabs(a[lc][COL]);
+#pragma unroll
+    for (int r = COL + 1; r < 7; ++r) {
+      const double t = fabs(a[lc][r]);
+      if (mag < t) { mag = t; best = r; }
+    }
+  }
+  const int src = (lane & ~1) | owner;
+  best = __shfl_sync(full, best, src);
+  mag = __shfl_sync(full, mag, src);
+  if (mag < 1e-12) generic = false;
+#pragma unroll
+  for (int r = COL + 1; r < 7; ++r) {
+    if (best == r) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) { const double t = a[q][COL]; a[q][COL] = a[q][r]; a[q][r] = t; }
+    }
+  }
+  const double p = __shfl_sync(full, a[lc][COL], src);
+  double m[7];
+#pragma unroll
+  for (int r = 0; r < 7; ++r) m[r] = (r == COL) ? 0.0 : __shfl_sync(full, a[lc][r], src);
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const int gc = 5 * h + q;
+    if (gc >= COL && gc < 9) {
+      a[q][COL] /= p;
+#pragma unroll
+      for (int r = 0; r < 7; ++r)
+        if (r != COL) a[q][r] -= m[r] * a[q][COL];
+    }
+  }
+}
+
 __device__ __noinline__ void wave_F_pairsolve(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int kend) {
   const int h = c.lane & 1;
   const int slot = c.lane >> 1;
   const int per_pass = c.nw * 16;
-  const unsigned full = 0xffffffffu;
 #pragma unroll 1
   for (int base = kbeg + c.wid * 16; base <= kend; base += per_pass) {
     const int k = base + slot;
@@ -183,63 +227,52 @@ __device__ __noinline__ void wave_F_pairsolve(const Ctx& c, const FParams& P, Wo
     int sel[7];
     minimal_sample<7>(P.seed, (uint32_t)(live ? k : kbeg), c.N, sel);
     double a[5][7];
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-      const int p = sel[r];
-      const double x1 = c.x1[p], y1 = c.y1[p], x2 = c.x2[p], y2 = c.y2[p];
-      if (h == 0) { a[0][r] = x2 * x1; a[1][r] = x2 * y1; a[2][r] = x2; a[3][r] = y2 * x1; a[4][r] = y2 * y1; }
-      else        { a[0][r] = y2;      a[1][r] = x1;      a[2][r] = y1; a[3][r] = 1.0;     a[4][r] = 0.0; }
+#define DG_PS_ROW(r)                                                                                             \
+    {                                                                                                            \
+      const int p = sel[r];                                                                                      \
+      const double x1 = c.x1[p], y1 = c.y1[p], x2 = c.x2[p], y2 = c.y2[p];                                       \
+      a[0][r] = h ? y2 : x2 * x1; a[1][r] = h ? x1 : x2 * y1; a[2][r] = h ? y1 : x2;                              \
+      a[3][r] = h ? 1.0 : y2 * x1; a[4][r] = h ? 0.0 : y2 * y1;                                                  \
     }
+    DG_PS_ROW(0) DG_PS_ROW(1) DG_PS_ROW(2) DG_PS_ROW(3) DG_PS_ROW(4) DG_PS_ROW(5) DG_PS_ROW(6)
+#undef DG_PS_ROW
     bool generic = true;
-#pragma unroll
-    for (int col = 0; col < 7; ++col) {
-      const int owner = (col < 5) ? 0 : 1;
-      const int lc = col - 5 * owner;
-      int best = col;
-      double mag = 0.0;
-      if (h == owner) {
-        mag = fabs(a[lc][col]);
-#pragma unroll
-        for (int r = col + 1; r < 7; ++r) {
-          const double t = fabs(a[lc][r]);
-          if (mag < t) { mag = t; best = r; }
-        }
-      }
-      const int src = (c.lane & ~1) | owner;
-      best = __shfl_sync(full, best, src);
-      mag = __shfl_sync(full, mag, src);
-      if (mag < 1e-12) generic = false;
-#pragma unroll
-      for (int r = col + 1; r < 7; ++r) {
-        if (best == r) {
-#pragma unroll
-          for (int q = 0; q < 5; ++q) { const double t = a[q][col]; a[q][col] = a[q][r]; a[q][r] = t; }
-        }
-      }
-      const double p = __shfl_sync(full, a[lc][col], src);
-      double m[7];
-#pragma unroll
-      for (int r = 0; r < 7; ++r) m[r] = (r == col) ? 0.0 : __shfl_sync(full, a[lc][r], src);
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const int gc = 5 * h + q;
-        if (gc >= col && gc < 9) {
-          a[q][col] /= p;
-#pragma unroll
-          for (int r = 0; r < 7; ++r)
-            if (r != col) a[q][r] -= m[r] * a[q][col];
-        }
-      }
-    }
+    pairsolve_step<0>(a, h, c.lane, generic);
+    pairsolve_step<1>(a, h, c.lane, generic);
+    pairsolve_step<2>(a, h, c.lane, generic);
+    pairsolve_step<3>(a, h, c.lane, generic);
+    pairsolve_step<4>(a, h, c.lane, generic);
+    pairsolve_step<5>(a, h, c.lane, generic);
+    pairsolve_step<6>(a, h, c.lane, generic);
     if (live && h == 1) {
       double* o = W.nsbuf + (size_t)(k - kbeg) * 16;
-#pragma unroll
-      for (int r = 0; r < 7; ++r) { o[r] = -a[2][r]; o[7 + r] = -a[3][r]; }
+      o[0] = -a[2][0]; o[1] = -a[2][1]; o[2] = -a[2][2]; o[3] = -a[2][3]; o[4] = -a[2][4]; o[5] = -a[2][5]; o[6] = -a[2][6];
+      o[7] = -a[3][0]; o[8] = -a[3][1]; o[9] = -a[3][2]; o[10] = -a[3][3]; o[11] = -a[3][4]; o[12] = -a[3][5]; o[13] = -a[3][6];
       o[14] = generic ? 1.0 : 0.0;
     }
   }
 }
 #endif
+
+// Null-space basis of a 7-point sample by the one-thread routine (host emulation; device: only the rare samples
+// whose pair elimination met a tiny pivot).  Returned by value so that the caller's copies stay in registers.
+struct NullPair { double v[18]; int n; };
+DG_ENGN NullPair nullspace_of_sample(const Ctx& c, int p0, int p1, int p2, int p3, int p4, int p5, int p6) {
+  double M[81], full[81];
+  const int ps[7] = {p0, p1, p2, p3, p4, p5, p6};
+  #pragma unroll 1
+  for (int i = 0; i < 7; ++i) {
+    const int p = ps[i];
+    f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], M + 9 * i);
+  }
+  #pragma unroll 1
+  for (int i = 63; i < 81; ++i) M[i] = 0.0;
+  NullPair r;
+  r.n = nullspace9(M, full);
+  #pragma unroll 1
+  for (int i = 0; i < 18; ++i) r.v[i] = full[i];
+  return r;
+}
 
 // ---------------------------------------------------------------------------------------------
 // WAVE: hypothesise iterations kbeg..kend (1-based), queue oriented-valid models, score them one
@@ -251,6 +284,11 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
                          bool* valid_itersam) {
   DG_SYNC();
   if (c.tid == 0) { c.sc->counter[0] = 0; c.sc->counter[1] = 0; c.sc->counter[2] = 0; }
+  // the minimal solvers gather 7 random correspondences per sample: pull the whole SoA (4 x N doubles) into L1 first
+  #pragma unroll 1
+  for (int i = c.tid * 16; i < c.N; i += c.nt * 16) {
+    prefetch_l1(c.x1 + i); prefetch_l1(c.y1 + i); prefetch_l1(c.x2 + i); prefetch_l1(c.y2 + i);
+  }
   DG_SYNC();
   // stage A: minimal solvers.  Device: A1 = two threads per sample eliminate in registers (wave_F_pairsolve),
   // A2 = one thread per sample takes the null-space basis through the cubic and the oriented test.
@@ -267,51 +305,51 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
   for (int k = kbeg + c.tid; k <= kend; k += c.nt) {
     int sel[7];
     minimal_sample<7>(P.seed, (uint32_t)k, c.N, sel);
-    double sol[18];
+    // every array below is indexed by literals only (after unrolling) so that it lives in registers
+    double f1[9], f2[9];
     int nullsize = 2;
 #if DG_DEVICE_PASS
     const double* ns = W.nsbuf + (size_t)(k - kbeg) * 16;
-    const bool generic = ns[14] != 0.0;
-    if (generic) {
-      for (int i = 0; i < 7; ++i) { sol[i] = ns[i]; sol[9 + i] = ns[7 + i]; }
-      sol[7] = 1.0; sol[8] = 0.0; sol[16] = 0.0; sol[17] = 1.0;
+    if (ns[14] != 0.0) {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { f1[i] = ns[i]; f2[i] = ns[7 + i]; }
+      f1[7] = 1.0; f1[8] = 0.0; f2[7] = 0.0; f2[8] = 1.0;
     } else
 #endif
     {
-      double M[81], full[81];
-      for (int i = 0; i < 7; ++i) {
-        const int p = sel[i];
-        f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], M + 9 * i);
-      }
-      #pragma unroll 1
-      for (int i = 63; i < 81; ++i) M[i] = 0.0;
-      nullsize = nullspace9(M, full);
-      #pragma unroll 1
-      for (int i = 0; i < 18; ++i) sol[i] = full[i];
+      const NullPair np = nullspace_of_sample(c, sel[0], sel[1], sel[2], sel[3], sel[4], sel[5], sel[6]);
+      nullsize = np.n;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { f1[i] = np.v[i]; f2[i] = np.v[9 + i]; }
     }
     if (nullsize != 2) continue;
     if (k == kIterSam) c.sc->counter[2] = 1;
-    double* f1 = sol;
-    double* f2 = sol + 9;
     double poly[4], roots[3];
-    seven_pt_cubic(f1, f2, poly);
-    const int nsol = cubic_real_roots(poly, roots);
-    double sx1[7], sy1[7], sx2[7], sy2[7];
+    seven_pt_cubic_inl(f1, f2, poly);
+    roots[1] = 0.0; roots[2] = 0.0;
+    const int nsol = cubic_real_roots_inl(poly, roots);
+    double sy1[7], sx2[7], sy2[7];
+#pragma unroll
     for (int t = 0; t < 7; ++t) {  // reference samidx order = reverse draw order
       const int p = sel[6 - t];
-      sx1[t] = c.x1[p]; sy1[t] = c.y1[p]; sx2[t] = c.x2[p]; sy2[t] = c.y2[p];
+      sy1[t] = c.y1[p]; sx2[t] = c.x2[p]; sy2[t] = c.y2[p];
     }
-    #pragma unroll 1
-    for (int i = 0; i < nsol; ++i) {
-      double f[9];
-      for (int j = 0; j < 9; ++j) f[j] = f1[j] * roots[i] + f2[j] * (1 - roots[i]);
-      if (!oriented_ok_F(f, sx1, sy1, sx2, sy2, 7)) continue;
-      const int slot = atomic_inc_shared(&c.sc->counter[0]);
-      if (slot < W.cand_cap) {
-        Cand& cd = W.cand[slot];
-        for (int j = 0; j < 9; ++j) cd.f[j] = f[j];
-        cd.k = k;
-        cd.root = i;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < nsol) {
+        double f[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) f[j] = f1[j] * roots[i] + f2[j] * (1 - roots[i]);
+        if (oriented_ok_F7(f, sy1, sx2, sy2)) {
+          const int slot = atomic_inc_shared(&c.sc->counter[0]);
+          if (slot < W.cand_cap) {
+            Cand& cd = W.cand[slot];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) cd.f[j] = f[j];
+            cd.k = k;
+            cd.root = i;
+          }
+        }
       }
     }
   }
@@ -510,7 +548,7 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
         ++st.non_degen;
         for (int t = 0; t < 7; ++t) st.samidxBest[t] = samidx[t];
         #pragma unroll 1
-        for (int j = c.tid; j < c.N; j += c.nt) W.errBest[j] = W.err[d][j];
+        for (int j = c.tid; j < c.N; j += c.nt) st_row(W.errBest + j, ld_row(W.err[d] + j));
         DG_SYNC();
         for (int j = 0; j < 9; ++j) st.FBest[j] = f[j];
       }

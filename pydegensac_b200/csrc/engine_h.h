@@ -28,7 +28,7 @@ struct HParams {
 DG_ENGN void blk_resid_H(const Ctx& c, int metric, const double* h, double* out) {
   HSym s;
   if (metric != H_SAMPSON) h_sym_prepare(h, &s);
-  for (int i = c.tid; i < c.N; i += c.nt) out[i] = h_resid_metric(metric, h, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+  for (int i = c.tid; i < c.N; i += c.nt) st_row(out + i, h_resid_metric(metric, h, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]));
   DG_SYNC();
 }
 // symmetric-transfer consistency count over a list (gate: always HDsSymMaxidx, exp_ranH.c:588-597)

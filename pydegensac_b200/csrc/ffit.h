@@ -45,10 +45,23 @@ struct FParams {
 };
 
 // ------------------------------------------------------------------ block-wide passes over the pair
+// Each thread works on TWO correspondences per trip: the residual is a long FP64 dependency chain (~80 operations,
+// 8-16 cycles each), two independent chains interleave in the pipe and their eight loads travel together.
 DG_ENGN void blk_resid_F(const Ctx& c, int metric, const double* F, double* out) {
   DG_PROF_BEGIN(19);
   DG_PROF_COUNT(20, 1);
-  for (int i = c.tid; i < c.N; i += c.nt) out[i] = f_resid(metric, F, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+  #pragma unroll 1
+  for (int i = c.tid; i < c.N; i += 2 * c.nt) {
+    const int j = i + c.nt;
+    const bool two = j < c.N;
+    const int jj = two ? j : i;
+    const double a1 = c.x1[i], b1 = c.y1[i], a2 = c.x2[i], b2 = c.y2[i];
+    const double p1 = c.x1[jj], q1 = c.y1[jj], p2 = c.x2[jj], q2 = c.y2[jj];
+    const double e0 = f_resid(metric, F, a1, b1, a2, b2);
+    const double e1 = f_resid(metric, F, p1, q1, p2, q2);
+    st_row(out + i, e0);
+    if (two) st_row(out + j, e1);
+  }
   DG_SYNC();
   DG_PROF_END(19);
 }
@@ -56,11 +69,18 @@ DG_ENGN void blk_resid_w_F(const Ctx& c, int metric, const double* F, double* ou
   DG_PROF_BEGIN(19);
   DG_PROF_COUNT(20, 1);
   #pragma unroll 1
-  for (int i = c.tid; i < c.N; i += c.nt) {
-    double e, ww;
-    f_resid_w(metric, F, c.x1[i], c.y1[i], c.x2[i], c.y2[i], &e, &ww);
-    out[i] = e;
-    w[i] = ww;
+  for (int i = c.tid; i < c.N; i += 2 * c.nt) {
+    const int j = i + c.nt;
+    const bool two = j < c.N;
+    const int jj = two ? j : i;
+    const double a1 = c.x1[i], b1 = c.y1[i], a2 = c.x2[i], b2 = c.y2[i];
+    const double p1 = c.x1[jj], q1 = c.y1[jj], p2 = c.x2[jj], q2 = c.y2[jj];
+    double e0, w0, e1, w1;
+    f_resid_w(metric, F, a1, b1, a2, b2, &e0, &w0);
+    f_resid_w(metric, F, p1, q1, p2, q2, &e1, &w1);
+    st_row(out + i, e0);
+    st_row(w + i, w0);
+    if (two) { st_row(out + j, e1); st_row(w + j, w1); }
   }
   DG_SYNC();
   DG_PROF_END(19);
@@ -84,7 +104,7 @@ DG_ENGN unsigned blk_sym_count_F(const Ctx& c, const double* F, const int* list,
 // to the list (which lives in L2: it was written by other warps a moment ago).
 template <int MAXS>
 __device__ __forceinline__ void warp_randsubset_core(int* list, int max_sz, int siz, uint64_t seed, uint32_t k, uint32_t j0,
-                                                     int lane, int (&drawn)[MAXS]) {
+                                                     int lane, int& mine) {
   const unsigned full = 0xffffffffu;
   int s = 0, top = 0, vs = 0, vt = 0;
   if (lane < siz) {
@@ -106,7 +126,7 @@ __device__ __forceinline__ void warp_randsubset_core(int* list, int max_sz, int 
     const bool live = q < siz;
     tp[2 * q] = live ? sq : -1;     tv[2 * q] = b;        // list[s]   <- value that sat at the top slot
     tp[2 * q + 1] = live ? tq : -1; tv[2 * q + 1] = a;    // list[top] <- the drawn value
-    drawn[q] = a;
+    if (lane == q) mine = a;                              // lane q keeps the value drawn at step q
   }
   if (lane < siz) {
     int fs = vs, ft = vt;
@@ -121,8 +141,8 @@ __device__ __forceinline__ void warp_randsubset_core(int* list, int max_sz, int 
 }
 template <int MAXS>
 __device__ __noinline__ void warp_randsubset(int* list, int max_sz, int siz, uint64_t seed, uint32_t k, uint32_t j0, int lane) {
-  int drawn[MAXS];
-  warp_randsubset_core<MAXS>(list, max_sz, siz, seed, k, j0, lane, drawn);
+  int mine = 0;
+  warp_randsubset_core<MAXS>(list, max_sz, siz, seed, k, j0, lane, mine);
 }
 #endif
 
@@ -390,13 +410,11 @@ DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double
   bool fast = true;
   if (c.wid == 0) {
     const unsigned full = 0xffffffffu;
-    int drawn[8];
-    warp_randsubset_core<8>(list, max_sz, 8, cur.seed, cur.k, cur.j, c.lane, drawn);
-    // correspondence of row i is list[max_sz - 8 + i] = the value drawn at step 7 - i
+    int mine = 0;
+    warp_randsubset_core<8>(list, max_sz, 8, cur.seed, cur.k, cur.j, c.lane, mine);
+    // correspondence of row i is list[max_sz - 8 + i] = the value drawn at step 7 - i (held by lane 7 - i)
     const int r = c.lane & 7;
-    int p = drawn[7];
-#pragma unroll
-    for (int q = 1; q < 8; ++q) if (r == q) p = drawn[7 - q];
+    const int p = __shfl_sync(full, mine, 7 - r);
     double m[9], n[9];
     f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], m);
     if (w) {
@@ -412,9 +430,11 @@ DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double
     }
     fast = null_8x9_core(m, c.lane, n);
     if (fast) {
-      enforce_rank2(n);
+      enforce_rank2_inl(n);
+      if (c.lane == 0) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) if (c.lane == i) c.sc->bc[i] = n[i];
+        for (int i = 0; i < 9; ++i) c.sc->bc[i] = n[i];
+      }
     }
     if (c.lane == 0) c.sc->bci[1] = fast ? 1 : 0;
   }

@@ -22,7 +22,7 @@ DG_HD void f_lin_row(double x1, double y1, double x2, double y2, double* row) {
 // discontinuous in F, so the coefficients are accumulated in the reference's TERM ORDER: with -fmad=false they
 // round identically to the x86-64 build.  Like the reference it REPLACES B by A - B afterwards, so that the
 // caller mixes f = A*r + B*(1-r)  (exp_ranF.c:1366-1368).
-DG_HDN void seven_pt_cubic(const double* A, double* B, double* p) {
+DG_HD void seven_pt_cubic_inl(const double* A, double* B, double* p) {
   const double a11 = A[0], a12 = A[1], a13 = A[2], a21 = A[3], a22 = A[4], a23 = A[5], a31 = A[6], a32 = A[7], a33 = A[8];
   double b11 = B[0], b12 = B[1], b13 = B[2], b21 = B[3], b22 = B[4], b23 = B[5], b31 = B[6], b32 = B[7], b33 = B[8];
   p[0] = -(b13 * b22 * b31) + b12 * b23 * b31 + b13 * b21 * b32 - b11 * b23 * b32 - b12 * b21 * b33 + b11 * b22 * b33;
@@ -43,10 +43,11 @@ DG_HDN void seven_pt_cubic(const double* A, double* B, double* p) {
   b11 = B[0]; b12 = B[1]; b13 = B[2]; b21 = B[3]; b22 = B[4]; b23 = B[5]; b31 = B[6]; b32 = B[7]; b33 = B[8];
   p[3] = -(b13 * b22 * b31) + b12 * b23 * b31 + b13 * b21 * b32 - b11 * b23 * b32 - b12 * b21 * b33 + b11 * b22 * b33;
 }
+DG_HDN void seven_pt_cubic(const double* A, double* B, double* p) { seven_pt_cubic_inl(A, B, p); }
 
 // Real roots of po[0] x^3 + po[1] x^2 + po[2] x + po[3] (Cardano / trigonometric), the branch
 // structure of the reference's rroots3 (Ftools.c:251-298): returns 1 or 3.
-DG_HDN int cubic_real_roots(const double* po, double* r) {
+DG_HD int cubic_real_roots_inl(const double* po, double* r) {
   const double third_pi = 1.0471975511965967;
   const double b = po[1] / po[0];
   const double c = po[2] / po[0];
@@ -77,6 +78,30 @@ DG_HDN int cubic_real_roots(const double* po, double* r) {
   r[1] = R2 * cos(third_pi - phit) - bt;
   r[2] = R2 * cos(third_pi + phit) - bt;
   return 3;
+}
+DG_HDN int cubic_real_roots(const double* po, double* r) { return cubic_real_roots_inl(po, r); }
+
+// oriented_ok_F for the 7-point sample with every index a literal (registers only); same tests, same order.
+DG_HD bool oriented_ok_F7(const double* F, const double (&sy1)[7], const double (&sx2)[7], const double (&sy2)[7]) {
+  const double xeps = 1.9984e-15;
+  double ec[3];
+  cross3(ec, F, F + 6);
+  bool big = false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if ((ec[i] > xeps) || (ec[i] < -xeps)) big = true;
+  if (!big) cross3(ec, F + 3, F + 6);
+  double sig1 = 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const double s1 = F[0] * sx2[i] + F[3] * sy2[i] + F[6] * 1.0;
+    const double s2 = ec[1] * 1.0 - ec[2] * sy1[i];
+    const double sig = s1 * s2;
+    if (i == 0) sig1 = sig;
+    else if (sig1 * sig < 0) ok = false;
+  }
+  return ok;
 }
 
 // Oriented epipolar constraint over the minimal sample (reference epipole/getorisig/all_ori_valid,

@@ -234,6 +234,34 @@ DG_HD bool smallest_right_sv3_fast(const double* F, double* v) {
 }
 
 // Rank-2 projection F <- U diag(s0,s1,0) V^T == F - (F v_min) v_min^T   (reference: singulF, Ftools.c:330-347)
+DG_HDN void enforce_rank2_slow(double* F) {
+  double G[9], V[9], sv[3];
+  svd3_onesided(F, G, V, sv);
+  int m = 0;
+  if (sv[1] < sv[m]) m = 1;
+  if (sv[2] < sv[m]) m = 2;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) F[3 * i + j] -= G[3 * i + m] * V[3 * j + m];
+}
+// inlinable flavour: the fast path keeps F in the caller's registers
+DG_HD void enforce_rank2_inl(double (&F)[9]) {
+  double v[3];
+  if (smallest_right_sv3_fast(F, v)) {
+    const double g0 = F[0] * v[0] + F[1] * v[1] + F[2] * v[2];
+    const double g1 = F[3] * v[0] + F[4] * v[1] + F[5] * v[2];
+    const double g2 = F[6] * v[0] + F[7] * v[1] + F[8] * v[2];
+    F[0] -= g0 * v[0]; F[1] -= g0 * v[1]; F[2] -= g0 * v[2];
+    F[3] -= g1 * v[0]; F[4] -= g1 * v[1]; F[5] -= g1 * v[2];
+    F[6] -= g2 * v[0]; F[7] -= g2 * v[1]; F[8] -= g2 * v[2];
+    return;
+  }
+  double T[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) T[i] = F[i];
+  enforce_rank2_slow(T);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) F[i] = T[i];
+}
 DG_HDN void enforce_rank2(double* F) {
   double v[3];
   if (smallest_right_sv3_fast(F, v)) {

@@ -147,40 +147,47 @@ DG_ENG inline double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu,
 // On the LO / DEGENSAC matrices of the benchmark scenes: 4.6 solves and 1.4 factorisations per call, no fallback.
 // Returns true with the unit eigenvector in ws->cs[0..8]; false (ws->A untouched) sends the caller to Jacobi.
 // ---------------------------------------------------------------------------------------------
+// One pivot of the L D L^T factorisation (template so that all indices into a[] are literals, cf. pairsolve_step).
+template <int K>
+__device__ __forceinline__ void eig9_factor_step(double (&a)[9], int lane, double tiny, bool& neg, double& dsel) {
+  double dk = shfl_d(a[K], K);
+  if (!(dk > tiny)) { dk = tiny; neg = true; }   // singular / negative pivot: regularise (and report)
+  const double inv = 1.0 / dk;
+  if (lane == K) { a[K] = dk; dsel = dk; }
+  const double lik = a[K] * inv;
+#pragma unroll
+  for (int j = K + 1; j < 9; ++j) {
+    const double akj = shfl_d(a[j], K);
+    if (lane > K) a[j] = fma(-lik, akj, a[j]);
+  }
+  if (lane > K) a[K] = lik;
+}
 __device__ __forceinline__ bool eig9_factor_reg(const double* A, int r, int lane, double sigma, double tiny,
                                                 double* T, double (&a)[9], double (&ct)[9], double& dinv) {
-#pragma unroll
-  for (int j = 0; j < 9; ++j) a[j] = A[r * 9 + j];
-#pragma unroll
-  for (int j = 0; j < 9; ++j) if (lane == j) a[j] -= sigma;
+  // (a lane-keyed select chain over a[] would be turned into a[lane] -- a dynamic index that drags the array
+  //  into local memory; every access keeps a literal index)
+  a[0] = A[r * 9 + 0] - ((lane == 0) ? sigma : 0.0); a[1] = A[r * 9 + 1] - ((lane == 1) ? sigma : 0.0);
+  a[2] = A[r * 9 + 2] - ((lane == 2) ? sigma : 0.0); a[3] = A[r * 9 + 3] - ((lane == 3) ? sigma : 0.0);
+  a[4] = A[r * 9 + 4] - ((lane == 4) ? sigma : 0.0); a[5] = A[r * 9 + 5] - ((lane == 5) ? sigma : 0.0);
+  a[6] = A[r * 9 + 6] - ((lane == 6) ? sigma : 0.0); a[7] = A[r * 9 + 7] - ((lane == 7) ? sigma : 0.0);
+  a[8] = A[r * 9 + 8] - ((lane == 8) ? sigma : 0.0);
   bool neg = false;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    double dk = shfl_d(a[k], k);
-    if (!(dk > tiny)) { dk = tiny; neg = true; }   // singular / negative pivot: regularise (and report)
-    const double inv = 1.0 / dk;
-    if (lane == k) a[k] = dk;
-    const double lik = a[k] * inv;
-#pragma unroll
-    for (int j = k + 1; j < 9; ++j) {
-      const double akj = shfl_d(a[j], k);
-      if (lane > k) a[j] -= lik * akj;
-    }
-    if (lane > k) a[k] = lik;
-  }
-  // lane i now holds L[i][k] (k < i) and d_i = a[i]; the transposed factor comes back through shared memory
-  double dsel = a[0];
-#pragma unroll
-  for (int j = 1; j < 9; ++j) if (lane == j) dsel = a[j];
+  double dsel = 1.0;
+  eig9_factor_step<0>(a, lane, tiny, neg, dsel); eig9_factor_step<1>(a, lane, tiny, neg, dsel);
+  eig9_factor_step<2>(a, lane, tiny, neg, dsel); eig9_factor_step<3>(a, lane, tiny, neg, dsel);
+  eig9_factor_step<4>(a, lane, tiny, neg, dsel); eig9_factor_step<5>(a, lane, tiny, neg, dsel);
+  eig9_factor_step<6>(a, lane, tiny, neg, dsel); eig9_factor_step<7>(a, lane, tiny, neg, dsel);
+  eig9_factor_step<8>(a, lane, tiny, neg, dsel);
+  // lane i now holds L[i][k] (k < i) and d_i; the transposed factor comes back through shared memory
   dinv = 1.0 / dsel;
   __syncwarp();
   if (lane < 9) {
-#pragma unroll
-    for (int j = 0; j < 9; ++j) T[lane * 9 + j] = a[j];
+    double* t = T + lane * 9;
+    t[0] = a[0]; t[1] = a[1]; t[2] = a[2]; t[3] = a[3]; t[4] = a[4]; t[5] = a[5]; t[6] = a[6]; t[7] = a[7]; t[8] = a[8];
   }
   __syncwarp();
-#pragma unroll
-  for (int k = 0; k < 9; ++k) ct[k] = T[k * 9 + r];      // L[k][i], used for k > i
+  ct[0] = T[0 * 9 + r]; ct[1] = T[1 * 9 + r]; ct[2] = T[2 * 9 + r]; ct[3] = T[3 * 9 + r]; ct[4] = T[4 * 9 + r];
+  ct[5] = T[5 * 9 + r]; ct[6] = T[6 * 9 + r]; ct[7] = T[7 * 9 + r]; ct[8] = T[8 * 9 + r];      // L[k][i], used for k > i
   return neg;
 }
 
@@ -213,7 +220,7 @@ __device__ __noinline__ bool warp_smallest_eigvec9_reg(WarpScratch* ws, int lane
 #pragma unroll
       for (int k = 8; k > 0; --k) {
         const double yk = shfl_d(y, k);
-        if (lane < k) y -= ct[k] * yk;
+        if (lane < k) y = fma(-ct[k], yk, y);
       }
       if (!act) y = 0.0;
       const double n2 = wl_sum(y * y);
@@ -225,13 +232,13 @@ __device__ __noinline__ bool warp_smallest_eigvec9_reg(WarpScratch* ws, int lane
 #pragma unroll
     for (int k = 0; k < 8; ++k) {           // forward substitution, unit lower factor
       const double yk = shfl_d(y, k);
-      if (lane > k) y -= a[k] * yk;
+      if (lane > k) y = fma(-a[k], yk, y);
     }
     y *= dinv;
 #pragma unroll
     for (int k = 8; k > 0; --k) {           // backward substitution, transposed factor
       const double yk = shfl_d(y, k);
-      if (lane < k) y -= ct[k] * yk;
+      if (lane < k) y = fma(-ct[k], yk, y);
     }
     if (!act) y = 0.0;
     const double n2 = wl_sum(y * y);
@@ -245,7 +252,7 @@ __device__ __noinline__ bool warp_smallest_eigvec9_reg(WarpScratch* ws, int lane
     if (it >= allow_at && ch > 1e-10 && nfac < 8) {
       double s = 0.0;
 #pragma unroll
-      for (int j = 0; j < 9; ++j) s += A[r * 9 + j] * shfl_d(x, j);
+      for (int j = 0; j < 9; ++j) s = fma(A[r * 9 + j], shfl_d(x, j), s);
       if (!act) s = 0.0;
       const double rho = wl_sum(s * x);
       const double rr = s - rho * x;
@@ -257,7 +264,7 @@ __device__ __noinline__ bool warp_smallest_eigvec9_reg(WarpScratch* ws, int lane
   // Rayleigh residual against the ORIGINAL matrix
   double s = 0.0;
 #pragma unroll
-  for (int j = 0; j < 9; ++j) s += A[r * 9 + j] * shfl_d(x, j);
+  for (int j = 0; j < 9; ++j) s = fma(A[r * 9 + j], shfl_d(x, j), s);
   if (!act) s = 0.0;
   const double rho = wl_sum(s * x);
   const double rr = s - rho * x;
@@ -299,7 +306,7 @@ __device__ __forceinline__ bool null_8x9_core(double (&m)[9], int lane, double (
 #pragma unroll
     for (int j = col + 1; j < 9; ++j) {
       const double pj = shfl_d(m[j], who) * inv;
-      if (r == who) m[j] = pj; else m[j] -= f * pj;
+      m[j] = (r == who) ? pj : fma(-f, pj, m[j]);
     }
     if (r == who) used = true;
   }
@@ -321,8 +328,10 @@ __device__ __noinline__ bool warp_null_8x9_reg(WarpScratch* ws, int lane) {
   for (int j = 0; j < 9; ++j) m[j] = ws->A[j * 8 + r];
   if (!null_8x9_core(m, lane, n)) return false;
   __syncwarp();
+  if (lane == 0) {
 #pragma unroll
-  for (int j = 0; j < 9; ++j) if (lane == j) ws->cs[j] = n[j];
+    for (int j = 0; j < 9; ++j) ws->cs[j] = n[j];
+  }
   __syncwarp();
   return true;
 }
