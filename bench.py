@@ -283,12 +283,16 @@ def run_gpu_arm(args):
             try:
                 from oracle import ref
                 if ref.available():
-                    cores = host_cores()
-                    rate, single, wall = cpu_reference_rate(args.cpu_pairs_per_core, cores)
-                    cpu = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                           "sample": "%d pairs per process x %d processes (one per core) of the same workload, "
-                                     "unmodified reference C core (oracle/_ref); single-process %.1f pairs/s"
-                                     % (args.cpu_pairs_per_core, cores, single)}
+                    # timed in a FRESH interpreter (the reference arm with one step): forking 16 workers out of
+                    # this process -- CUDA context, pinned staging buffers, sampler thread -- halves their speed
+                    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", "1",
+                                          "--steps", "1", "--warmup", "1", "--cpu-pairs-per-core",
+                                          str(args.cpu_pairs_per_core)], capture_output=True, text=True, timeout=900,
+                                         env={k: v for k, v in os.environ.items()
+                                              if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")})
+                    ref_line = json.loads(out.stdout.strip().splitlines()[-1])
+                    cpu = ref_line["cpu_baseline"]
+                    cpu["sample"] += " (separate process, 1 timed step after 1 warm-up step)"
             except Exception as ex:  # pragma: no cover
                 cpu = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
         sm = sorted(sampler.samples)
@@ -324,7 +328,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=4096)
+    ap.add_argument("--pairs-per-gpu", type=int, default=8192)
     ap.add_argument("--cpu-pairs-per-core", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

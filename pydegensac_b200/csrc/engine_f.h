@@ -375,12 +375,21 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
         float J = 0.0f;
         const Pt32* pts = c.t32->pts;
 #if DG_DEVICE_PASS
-        for (int i = c.lane; i < c.N; i += 32) {
-#else
-        for (int i = 0; i < c.N; ++i) {
-#endif
-          J += f_filter_gain(ff, pts[i]);
+        {  // four independent gain chains per lane (sqrt + divide each): the loop is latency-, not issue-bound
+          float J1 = 0.0f, J2 = 0.0f, J3 = 0.0f;
+          int i = c.lane;
+          #pragma unroll 1
+          for (; i + 96 < c.N; i += 128) {
+            const Pt32 p0 = pts[i], p1 = pts[i + 32], p2 = pts[i + 64], p3 = pts[i + 96];
+            J += f_filter_gain(ff, p0); J1 += f_filter_gain(ff, p1); J2 += f_filter_gain(ff, p2); J3 += f_filter_gain(ff, p3);
+          }
+          #pragma unroll 1
+          for (; i < c.N; i += 32) J += f_filter_gain(ff, pts[i]);
+          J = (J + J1) + (J2 + J3);
         }
+#else
+        for (int i = 0; i < c.N; ++i) J += f_filter_gain(ff, pts[i]);
+#endif
 #if DG_DEVICE_PASS
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) J += __shfl_xor_sync(0xffffffffu, J, o);

@@ -411,7 +411,10 @@ DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double
   if (c.wid == 0) {
     const unsigned full = 0xffffffffu;
     int mine = 0;
+    DG_PROF_BEGIN(41);
     warp_randsubset_core<8>(list, max_sz, 8, cur.seed, cur.k, cur.j, c.lane, mine);
+    DG_PROF_END(41);
+    DG_PROF_BEGIN(42);
     // correspondence of row i is list[max_sz - 8 + i] = the value drawn at step 7 - i (held by lane 7 - i)
     const int r = c.lane & 7;
     const int p = __shfl_sync(full, mine, 7 - r);
@@ -428,7 +431,11 @@ DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double
         if (src < 8) m[t] *= wv;
       }
     }
+    DG_PROF_END(42);
+    DG_PROF_BEGIN(43);
     fast = null_8x9_core(m, c.lane, n);
+    DG_PROF_END(43);
+    DG_PROF_BEGIN(44);
     if (fast) {
       enforce_rank2_inl(n);
       if (c.lane == 0) {
@@ -437,8 +444,11 @@ DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double
       }
     }
     if (c.lane == 0) c.sc->bci[1] = fast ? 1 : 0;
+    DG_PROF_END(44);
   }
+  DG_PROF_BEGIN(45);
   DG_SYNC();
+  DG_PROF_END(45);
   fast = c.sc->bci[1] != 0;
   cur.j += 8u;
   if (fast) {

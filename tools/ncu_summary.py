@@ -53,7 +53,7 @@ try:
         f = l.split()
         if len(f) >= 8 and f[3] == "FUNC" and kind in f[7]:
             m = re.search(r"\$_ZN2dg\d+([A-Za-z_0-9]+?)E", f[7])
-            syms.append((int(f[1], 16), int(f[2]), m.group(1) if m else f[7][-32:]))
+            syms.append((int(f[1], 16), int(f[2], 0), m.group(1) if m else f[7][-32:]))
     syms.sort()
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     srows = list(csv.reader(io.StringIO(src)))
