@@ -102,9 +102,20 @@ DG_ENGN unsigned blk_sym_count_F(const Ctx& c, const double* F, const int* list,
 // override earlier ones, as in minimal_sample -- by every lane redundantly, and each lane stores the final value of
 // the two positions it touched.  Same result as the sequential loop below, without eight dependent round trips
 // to the list (which lives in L2: it was written by other warps a moment ago).
-template <int MAXS>
-__device__ __forceinline__ void warp_randsubset_core(int* list, int max_sz, int siz, uint64_t seed, uint32_t k, uint32_t j0,
-                                                     int lane, int& mine) {
+// Latest logged value of position P, or `dflt` when P was never written: log entry t lives on lane t (tp = position,
+// tv = value, tp = -1 when empty); entries are appended in lane order, so the highest matching lane is the latest.
+__device__ __forceinline__ int log_lookup(int tp, int tv, int P, int dflt) {
+  const unsigned m = __ballot_sync(0xffffffffu, tp == P);
+  const int v = __shfl_sync(0xffffffffu, tv, m ? 31 - __clz(m) : 0);
+  return m ? v : dflt;
+}
+// randsubset on one warp (siz <= 16), COMPACT: lane i < siz generates draw i and prefetches both entries of its swap;
+// the swaps are replayed in order on a log of (position, value) writes that is spread over the lanes (two entries
+// per step), so the loop body is a handful of ballots and shuffles; each lane then stores the final value of the two
+// positions it touched.  Returns in `mine` (lane q) the value drawn at step q = the entry list[max_sz - 1 - q].
+// (An earlier version kept the log in registers and unrolled the O(siz^2) compare chains: 2-8 KB... 32 KB of
+// straight-line code per call, which on B200 costs ~6 cycles per instruction to stream -- see DESIGN.md.)
+__device__ __noinline__ int warp_subset_draw(int* list, int max_sz, int siz, uint64_t seed, uint32_t k, uint32_t j0, int lane) {
   const unsigned full = 0xffffffffu;
   int s = 0, top = 0, vs = 0, vt = 0;
   if (lane < siz) {
@@ -113,36 +124,25 @@ __device__ __forceinline__ void warp_randsubset_core(int* list, int max_sz, int 
     vs = list[s];
     vt = list[top];
   }
-  int tp[2 * MAXS], tv[2 * MAXS];
-#pragma unroll
-  for (int q = 0; q < MAXS; ++q) {
+  int tp = -1, tv = 0, mine = 0;
+  #pragma unroll 1
+  for (int q = 0; q < siz; ++q) {
     const int sq = __shfl_sync(full, s, q), tq = __shfl_sync(full, top, q);
-    int a = __shfl_sync(full, vs, q), b = __shfl_sync(full, vt, q);
-#pragma unroll
-    for (int t = 0; t < 2 * q; ++t) {
-      if (tp[t] == sq) a = tv[t];
-      if (tp[t] == tq) b = tv[t];
-    }
-    const bool live = q < siz;
-    tp[2 * q] = live ? sq : -1;     tv[2 * q] = b;        // list[s]   <- value that sat at the top slot
-    tp[2 * q + 1] = live ? tq : -1; tv[2 * q + 1] = a;    // list[top] <- the drawn value
-    if (lane == q) mine = a;                              // lane q keeps the value drawn at step q
+    const int a = log_lookup(tp, tv, sq, __shfl_sync(full, vs, q));
+    const int b = log_lookup(tp, tv, tq, __shfl_sync(full, vt, q));
+    if (lane == 2 * q) { tp = sq; tv = b; }          // list[s]   <- value that sat at the top slot
+    if (lane == 2 * q + 1) { tp = tq; tv = a; }      // list[top] <- the drawn value
+    if (lane == q) mine = a;
   }
-  if (lane < siz) {
-    int fs = vs, ft = vt;
-#pragma unroll
-    for (int t = 0; t < 2 * MAXS; ++t) {
-      if (tp[t] == s) fs = tv[t];
-      if (tp[t] == top) ft = tv[t];
-    }
-    list[s] = fs;
-    list[top] = ft;
+  int fs = vs, ft = vt;
+  #pragma unroll 1
+  for (int q = 0; q < siz; ++q) {
+    const int a = log_lookup(tp, tv, __shfl_sync(full, s, q), __shfl_sync(full, vs, q));
+    const int b = log_lookup(tp, tv, __shfl_sync(full, top, q), __shfl_sync(full, vt, q));
+    if (lane == q) { fs = a; ft = b; }
   }
-}
-template <int MAXS>
-__device__ __noinline__ void warp_randsubset(int* list, int max_sz, int siz, uint64_t seed, uint32_t k, uint32_t j0, int lane) {
-  int mine = 0;
-  warp_randsubset_core<MAXS>(list, max_sz, siz, seed, k, j0, lane, mine);
+  if (lane < siz) { list[s] = fs; list[top] = ft; }
+  return mine;
 }
 #endif
 
@@ -152,10 +152,8 @@ DG_ENGN void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCu
   DG_PROF_BEGIN(23);
   DG_SYNC();
 #if DG_DEVICE_PASS
-  if (siz <= 8) {
-    if (c.wid == 0) warp_randsubset<8>(list, max_sz, siz, cur.seed, cur.k, cur.j, c.lane);
-  } else if (siz <= 14) {
-    if (c.wid == 0) warp_randsubset<14>(list, max_sz, siz, cur.seed, cur.k, cur.j, c.lane);
+  if (siz <= 16) {
+    if (c.wid == 0) (void)warp_subset_draw(list, max_sz, siz, cur.seed, cur.k, cur.j, c.lane);
   } else
 #endif
   if (c.tid == 0) {
@@ -404,21 +402,25 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
 // ---------------------------------------------------------------------------------------------
 DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double* w, DrawCursor& cur, double* f) {
 #if DG_DEVICE_PASS
+  // COMPACT CODE ON PURPOSE.  The first version of this routine unrolled everything (76 KB of straight-line code) and
+  // ran at the instruction-fetch limit (~6 cycles per instruction); here every stage is a short rolled loop whose
+  // register arrays are only ever indexed by literals: the swap log is spread over the lanes, the elimination
+  // rotates its row so that the pivot column is always m[0].
   DG_PROF_BEGIN(7);
   DG_PROF_COUNT(27, 1);
   DG_SYNC();
   bool fast = true;
   if (c.wid == 0) {
     const unsigned full = 0xffffffffu;
-    int mine = 0;
+    const int lane = c.lane;
     DG_PROF_BEGIN(41);
-    warp_randsubset_core<8>(list, max_sz, 8, cur.seed, cur.k, cur.j, c.lane, mine);
+    const int mine = warp_subset_draw(list, max_sz, 8, cur.seed, cur.k, cur.j, lane);
     DG_PROF_END(41);
     DG_PROF_BEGIN(42);
-    // correspondence of row i is list[max_sz - 8 + i] = the value drawn at step 7 - i (held by lane 7 - i)
-    const int r = c.lane & 7;
+    // ---- rows: correspondence of row i is list[max_sz - 8 + i] = the value drawn at step 7 - i (held by lane 7 - i)
+    const int r = lane & 7;
     const int p = __shfl_sync(full, mine, 7 - r);
-    double m[9], n[9];
+    double m[9];
     f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], m);
     if (w) {
       // the reference scales the row-major 9 x 8 array with stride 9 (Ftools.c:431): entry (coefficient t, row i)
@@ -431,19 +433,57 @@ DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double
         if (src < 8) m[t] *= wv;
       }
     }
+    // ---- Gauss-Jordan with partial pivoting by role; after every column the row is rotated left, so the pivot
+    //      column is m[0], the right-hand side ends in m[0] after eight steps, zeros are shifted in behind it
+    bool used = false;
+    int mycol = 8;
     DG_PROF_END(42);
     DG_PROF_BEGIN(43);
-    fast = null_8x9_core(m, c.lane, n);
+    #pragma unroll 1
+    for (int col = 0; col < 8; ++col) {
+      double mag = used ? -1.0 : fabs(m[0]);
+      if (!(mag == mag)) mag = 1e308 * 10.0;   // NaN -> +inf: wins the search and fails the test below
+      int who = r;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const double m2 = __shfl_xor_sync(full, mag, o);
+        const int w2 = __shfl_xor_sync(full, who, o);
+        if (m2 > mag || (m2 == mag && w2 < who)) { mag = m2; who = w2; }
+      }
+      if (!(mag > 0.0) || !(mag < 1e300)) { fast = false; break; }
+      const double inv = 1.0 / shfl_d(m[0], who);
+      const double fm = m[0];
+      const bool piv = (r == who);
+#pragma unroll
+      for (int j = 1; j < 9; ++j) {
+        const double pj = shfl_d(m[j], who) * inv;
+        m[j - 1] = piv ? pj : fma(-fm, pj, m[j]);      // eliminate and rotate in one go
+      }
+      m[8] = 0.0;
+      if (piv) { used = true; mycol = col; }
+    }
     DG_PROF_END(43);
     DG_PROF_BEGIN(44);
     if (fast) {
+      double n2 = m[0] * m[0];
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) n2 += __shfl_xor_sync(full, n2, o);
+      const double sc = rsqrt(1.0 + n2);
+      WarpScratch* ws = &c.sc->ws[0];
+      __syncwarp();
+      if (lane < 8) ws->cs[mycol] = -m[0] * sc;
+      if (lane == 8) ws->cs[8] = sc;
+      __syncwarp();
+      double n[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) n[i] = ws->cs[i];
       enforce_rank2_inl(n);
-      if (c.lane == 0) {
+      if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) c.sc->bc[i] = n[i];
       }
     }
-    if (c.lane == 0) c.sc->bci[1] = fast ? 1 : 0;
+    if (lane == 0) c.sc->bci[1] = fast ? 1 : 0;
     DG_PROF_END(44);
   }
   DG_PROF_BEGIN(45);
@@ -488,7 +528,7 @@ DG_ENGN bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, const 
         const int nxt = base + 32 + c.lane;
         const uint32_t vn = (nxt < n) ? (uint32_t)list[nxt] : 0u;
         if (n - base >= 32) {
-#pragma unroll
+#pragma unroll 4
           for (int j = 0; j < 32; ++j) h = sfh_word(h, __shfl_sync(full, v, j));
         } else {
           #pragma unroll 1
