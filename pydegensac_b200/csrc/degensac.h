@@ -591,13 +591,29 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
       f_from_plane_parallax(H, c.x1[a], c.y1[a], c.x2[a], c.y2[a], c.x1[b], c.y1[b], c.x2[b], c.y2[b], aF);
       int cnt = 0;
 #if DG_DEVICE_PASS
-      for (int i = c.lane; i < nN; i += 32) {
+      {  // two gathers + two residual chains in flight per lane
+        int i = c.lane;
+        #pragma unroll 1
+        for (; i + 32 < nN; i += 64) {
+          const int p = uN[i], q = uN[i + 32];
+          const double a1 = c.x1[p], b1 = c.y1[p], a2 = c.x2[p], b2 = c.y2[p];
+          const double e1 = c.x1[q], g1 = c.y1[q], e2 = c.x2[q], g2 = c.y2[q];
+          const double r0 = f_resid_sampson(aF, a1, b1, a2, b2);
+          const double r1 = f_resid_sampson(aF, e1, g1, e2, g2);
+          if (r0 < th2) ++cnt;
+          if (r1 < th2) ++cnt;
+        }
+        if (i < nN) {
+          const int p = uN[i];
+          if (f_resid_sampson(aF, c.x1[p], c.y1[p], c.x2[p], c.y2[p]) < th2) ++cnt;
+        }
+      }
 #else
       for (int i = 0; i < nN; ++i) {
-#endif
         const int p = uN[i];
         if (f_resid_sampson(aF, c.x1[p], c.y1[p], c.x2[p], c.y2[p]) < th2) ++cnt;
       }
+#endif
       cnt = warp_sum_i(cnt);
       if (c.lane == 0) counts[s] = cnt;
     }

@@ -358,13 +358,16 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
           for (int k = 0; k < 9; ++k) r[q][k] = 0.0;
         }
       }
+      // every lane holds the warp total after the butterfly; lane (t mod 32) owns entry t, so the 45 slot updates
+      // are spread over the lanes instead of queueing on lane 0
 #pragma unroll
       for (int i = 0; i < 9; ++i)
 #pragma unroll
         for (int jj = 0; jj <= i; ++jj) {
           double sum = r[0][i] * r[0][jj] + r[1][i] * r[1][jj] + r[2][i] * r[2][jj];
           sum = warp_sum(sum);
-          if (c.lane == 0) slot[i * (i + 1) / 2 + jj] += sum;
+          constexpr int W32 = DG_DEVICE_PASS ? 32 : 1;
+          if (c.lane == (i * (i + 1) / 2 + jj) % W32) slot[i * (i + 1) / 2 + jj] += sum;
         }
     }
     DG_SYNC();
