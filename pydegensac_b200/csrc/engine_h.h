@@ -28,7 +28,16 @@ struct HParams {
 DG_ENGN void blk_resid_H(const Ctx& c, int metric, const double* h, double* out) {
   HSym s;
   if (metric != H_SAMPSON) h_sym_prepare(h, &s);
-  for (int i = c.tid; i < c.N; i += c.nt) st_row(out + i, h_resid_metric(metric, h, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]));
+  #pragma unroll 1
+  for (int i = c.tid; i < c.N; i += 2 * c.nt) {   // two independent residual chains per trip (cf. blk_resid_F)
+    const int j = i + c.nt;
+    const bool two = j < c.N;
+    const int jj = two ? j : i;
+    const double e0 = h_resid_metric(metric, h, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+    const double e1 = h_resid_metric(metric, h, s, c.x1[jj], c.y1[jj], c.x2[jj], c.y2[jj]);
+    st_row(out + i, e0);
+    if (two) st_row(out + j, e1);
+  }
   DG_SYNC();
 }
 // symmetric-transfer consistency count over a list (gate: always HDsSymMaxidx, exp_ranH.c:588-597)

@@ -122,28 +122,57 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
   if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
   A1[1] *= -A1[0]; A1[2] *= -A1[0];
   A2[1] *= -A2[0]; A2[2] *= -A2[0];
-  #pragma unroll 1
-  for (int i = 0; i < 45; ++i) v[i] = 0.0;
-  #pragma unroll 1
-  for (int j = c.tid; j < len; j += c.nt) {
-    const int p = idx[j];
-    double a[3], b[3], r0[9], r1[9];
-    a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
-    b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
-    for (int t = 0; t < 3; ++t) {  // reference lin_hgN, Htools.c:60-99
-      r0[3 * t] = b[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a[0] * b[t];
-      r1[3 * t] = 0.0;  r1[3 * t + 1] = b[t]; r1[3 * t + 2] = -a[1] * b[t];
-    }
-    int t = 0;
-    for (int i = 0; i < 9; ++i)
-      #pragma unroll 1
-      for (int jj = 0; jj <= i; ++jj) {
-        v[t] += r0[i] * r0[jj];
-        v[t] += r1[i] * r1[jj];
-        ++t;
+  // Normal matrix of the 2 x len DLT rows (reference lin_hgN + cov_mat, Htools.c:60-99).  The two rows of a
+  // correspondence are r0 = (b0,0,-a0 b0, b1,0,-a0 b1, b2,0,-a0 b2) and r1 = (0,b0,-a1 b0, 0,b1,-a1 b1, 0,b2,-a1 b2):
+  // nine of the 45 entries are structurally zero and every other entry has one or two non-zero products.  Each
+  // thread accumulates the 36 live entries in REGISTERS (literal indices only: a 45-entry accumulator indexed by a
+  // running counter lived in local memory), then each entry is reduced across the warp, lane (t mod 32) adds it to
+  // the warp's slot, and the slots are combined after the barrier.
+  {
+    double acc[45];
+#pragma unroll
+    for (int t = 0; t < 45; ++t) acc[t] = 0.0;
+    #pragma unroll 1
+    for (int j = c.tid; j < len; j += c.nt) {
+      const int p = idx[j];
+      const double a0 = c.x1[p] * A1[0] + A1[1], a1 = c.y1[p] * A1[0] + A1[2];
+      double bb[3];
+      bb[0] = c.x2[p] * A2[0] + A2[1]; bb[1] = c.y2[p] * A2[0] + A2[2]; bb[2] = 1.0;
+      double r0[9], r1[9];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        r0[3 * t] = bb[t]; r0[3 * t + 1] = 0.0; r0[3 * t + 2] = -a0 * bb[t];
+        r1[3 * t] = 0.0;   r1[3 * t + 1] = bb[t]; r1[3 * t + 2] = -a1 * bb[t];
       }
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int jj = 0; jj <= i; ++jj) {
+          if (i % 3 != 1 && jj % 3 != 1) acc[i * (i + 1) / 2 + jj] += r0[i] * r0[jj];
+          if (i % 3 != 0 && jj % 3 != 0) acc[i * (i + 1) / 2 + jj] += r1[i] * r1[jj];
+        }
+    }
+    double* slot = c.sc->vec + c.wid * kVecRed;
+    DG_SYNC();
+    constexpr int W32 = DG_DEVICE_PASS ? 32 : 1;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+      for (int jj = 0; jj <= i; ++jj) {
+        const bool live = (i % 3 != 1 && jj % 3 != 1) || (i % 3 != 0 && jj % 3 != 0);
+        const double sum = live ? warp_sum(acc[i * (i + 1) / 2 + jj]) : 0.0;
+        if (c.lane == (i * (i + 1) / 2 + jj) % W32) slot[i * (i + 1) / 2 + jj] = sum;
+      }
+    DG_SYNC();
+    #pragma unroll 1
+    for (int t = c.tid; t < 45; t += c.nt) {
+      double sum = 0.0;
+      #pragma unroll 1
+      for (int wv = 0; wv < c.nw; ++wv) sum += c.sc->vec[wv * kVecRed + t];
+      c.sc->vec_out[t] = sum;
+    }
+    DG_SYNC();
   }
-  blk_sum_vec(c, v, 45);
   if (c.wid == 0) {
     WarpScratch* ws = &c.sc->ws[0];
     warp_min_eigvec9_packed(ws, c.sc->vec_out, c.lane, DG_DEVICE_PASS ? 32 : 1);
