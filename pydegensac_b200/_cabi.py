@@ -84,7 +84,7 @@ def fundamental_batch(pts1, pts2, px_th, conf, max_iters, error_type, sym_check,
                                              _p(F, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32))
     if rc != 0:
         _raise(rc)
-    return F, mask.astype(bool), stats
+    return F, mask.view(np.bool_), stats
 
 
 def homography_batch(pts1, pts2, px_th, conf, max_iters, error_type, sym_check, laf_coef, seeds):
@@ -101,7 +101,7 @@ def homography_batch(pts1, pts2, px_th, conf, max_iters, error_type, sym_check, 
                                             _p(H, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32))
     if rc != 0:
         _raise(rc)
-    return H, mask.astype(bool), stats
+    return H, mask.view(np.bool_), stats
 
 
 def fundamental_batch_dev(d_p1, d_p2, P, N, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check,

@@ -79,6 +79,8 @@ struct BatchArgs {
   int* work_counter;
   int pts_in_smem;
   int tile32_in_smem;   // FP32 filter tile placement (F path)
+  const int* ready;     // host-buffer flavour: number of leading pairs whose input has landed in HBM (nullptr: all)
+  int* status;          // [0] = 1 when a CTA gave up waiting for its input
 };
 
 template <int KIND>  // 0: fundamental matrix, 1: homography
@@ -112,6 +114,23 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
     __syncthreads();
     const int p = s_pair;
     if (p >= a.n_pairs) break;
+    if (a.ready) {
+      // The host streams the batch in chunks on a copy stream while this kernel runs and bumps `ready` after each
+      // chunk.  Bounded wait (~4 s): a broken feed must never hang the GPU.
+      __shared__ int s_ok;
+      if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        int ok = 1;
+        while (*reinterpret_cast<const volatile int*>(a.ready) <= p) {
+          __nanosleep(500);
+          if (clock64() - t0 > (1LL << 33)) { ok = 0; break; }
+        }
+        if (!ok) a.status[0] = 1;
+        s_ok = ok;
+      }
+      __syncthreads();
+      if (!s_ok) break;
+    }
     // ---- stage the pair: HBM -> SoA tile
     const double* g1 = a.x1y1 + (size_t)p * n * a.dim;
     const double* g2 = a.x2y2 + (size_t)p * n * a.dim;
@@ -119,7 +138,7 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
       const double2* v1 = reinterpret_cast<const double2*>(g1);
       const double2* v2 = reinterpret_cast<const double2*>(g2);
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double2 q1 = __ldg(v1 + i), q2 = __ldg(v2 + i);
+        const double2 q1 = __ldcg(v1 + i), q2 = __ldcg(v2 + i);   // L2 only: the chunk may have landed after this kernel started
         soa[i] = q1.x; soa[row + i] = q1.y; soa[2 * row + i] = q2.x; soa[3 * row + i] = q2.y;
       }
     } else {
@@ -168,8 +187,12 @@ struct Cache {
   unsigned char* ws = nullptr; size_t ws_bytes = 0;
   int* counter = nullptr;
   unsigned char* io = nullptr; size_t io_bytes = 0;   // staging for the host-buffer flavour
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_feed = nullptr;
+  cudaStream_t s_run = nullptr, s_copy = nullptr;     // host-buffer flavour: kernel stream + input feed stream
+  int* ready = nullptr;                               // device: pairs whose input has landed; status word follows
+  int* h_ready = nullptr;                             // pinned: cumulative pair counts per chunk
 };
+constexpr int kMaxChunks = 16;
 std::mutex g_mu;
 Cache g_c;
 char g_err[512] = "";
@@ -201,14 +224,20 @@ int ensure_device() {
   g_c.smem_optin = prop.sharedMemPerBlockOptin;
   CU(cudaEventCreate(&g_c.ev0));
   CU(cudaEventCreate(&g_c.ev1));
+  CU(cudaEventCreateWithFlags(&g_c.ev_feed, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&g_c.s_run, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g_c.s_copy, cudaStreamNonBlocking));
+  CU(cudaMalloc(&g_c.ready, 2 * sizeof(int)));
+  CU(cudaHostAlloc(&g_c.h_ready, kMaxChunks * sizeof(int), cudaHostAllocDefault));
   return 0;
 }
 
 template <int KIND>
 int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, double px_th, double conf, int max_iters,
            int metric, int sym_check, int degen, const unsigned long long* d_seeds, double* d_model,
-           unsigned char* d_mask, int* d_stats, cudaStream_t st) {
+           unsigned char* d_mask, int* d_stats, cudaStream_t st, const int* d_ready = nullptr, int* d_status = nullptr) {
   BatchArgs a;
+  a.ready = d_ready; a.status = d_status;
   a.x1y1 = d1; a.x2y2 = d2; a.n_pairs = n_pairs; a.n = n; a.dim = dim;
   a.px_th = px_th; a.conf = conf; a.laf_coef = 0.0; a.max_iters = max_iters; a.metric = metric;
   a.sym_check = sym_check; a.degen = degen; a.seeds = d_seeds;
@@ -302,19 +331,49 @@ int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim
   double* dmodel = (double*)p; p += model_b;
   unsigned char* dmask = p; p += mask_b;
   int* dstats = (int*)p;
-  cudaStream_t st = 0;
-  CU(cudaMemcpyAsync(d1, x1y1, sizeof(double) * (size_t)n_pairs * n * dim, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d2, x2y2, sizeof(double) * (size_t)n_pairs * n * dim, cudaMemcpyHostToDevice, st));
-  if (seeds) CU(cudaMemcpyAsync(dseed, seeds, sizeof(uint64_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, st));
+  // Input feed overlapped with the kernel: the batch is copied in chunks on a copy stream; after every chunk the
+  // device-side `ready` count is bumped (a 4-byte copy from pinned memory, ordered behind the chunk) and the
+  // persistent CTAs wait on it before staging a pair.  Chunk 0 covers at least two pairs per CTA.
+  cudaStream_t st = g_c.s_run, cs = g_c.s_copy;
+  const size_t pair_elems = (size_t)n * dim;
+  int nchunks = 8;
+  int first = 2 * 2 * g_c.sm_count;
+  if (first > n_pairs) first = n_pairs;
+  int rest = n_pairs - first;
+  if (rest <= 0) nchunks = 1;
+  const int per = (nchunks > 1) ? (rest + (nchunks - 2)) / (nchunks - 1) : 0;
+  CU(cudaMemsetAsync(g_c.ready, 0, 2 * sizeof(int), cs));
+  if (seeds) CU(cudaMemcpyAsync(dseed, seeds, sizeof(uint64_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cs));
+  CU(cudaEventRecord(g_c.ev_feed, cs));
+  CU(cudaStreamWaitEvent(st, g_c.ev_feed, 0));
   CU(cudaEventRecord(g_c.ev0, st));
   rc = launch<KIND>(d1, d2, n_pairs, n, dim, px_th, conf, max_iters, metric, sym_check, degen, seeds ? dseed : nullptr,
-                    dmodel, dmask, dstats, st);
+                    dmodel, dmask, dstats, st, g_c.ready, g_c.ready + 1);
   if (rc) return rc;
   CU(cudaEventRecord(g_c.ev1, st));
+  int done = 0;
+  for (int ci = 0; ci < nchunks && done < n_pairs; ++ci) {
+    int cnt = (ci == 0) ? first : per;
+    if (done + cnt > n_pairs) cnt = n_pairs - done;
+    const size_t off = (size_t)done * pair_elems;
+    const cudaError_t e1 = cudaMemcpyAsync(d1 + off, x1y1 + off, sizeof(double) * (size_t)cnt * pair_elems, cudaMemcpyHostToDevice, cs);
+    const cudaError_t e2 = cudaMemcpyAsync(d2 + off, x2y2 + off, sizeof(double) * (size_t)cnt * pair_elems, cudaMemcpyHostToDevice, cs);
+    done += cnt;
+    g_c.h_ready[ci] = (e1 == cudaSuccess && e2 == cudaSuccess) ? done : n_pairs + 1;   // on a failed copy release the CTAs anyway
+    cudaMemcpyAsync(g_c.ready, &g_c.h_ready[ci], sizeof(int), cudaMemcpyHostToDevice, cs);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      cudaStreamSynchronize(cs); cudaStreamSynchronize(st);
+      return fail(DGB200_E_CUDA, "input copy failed", e1 != cudaSuccess ? e1 : e2);
+    }
+  }
   CU(cudaMemcpyAsync(model_out, dmodel, sizeof(double) * 9 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(mask_out, dmask, (size_t)n_pairs * n, cudaMemcpyDeviceToHost, st));
   if (stats_out) CU(cudaMemcpyAsync(stats_out, dstats, sizeof(int) * 4 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+  int h_status[2] = {0, 0};
+  CU(cudaMemcpyAsync(h_status, g_c.ready, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(cs));
   CU(cudaStreamSynchronize(st));
+  if (h_status[1] != 0) return fail(DGB200_E_CUDA, "input feed timed out inside the kernel");
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, g_c.ev0, g_c.ev1));
   g_last_ms = ms;
