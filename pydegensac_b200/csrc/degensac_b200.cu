@@ -80,7 +80,8 @@ struct BatchArgs {
   int pts_in_smem;
   int tile32_in_smem;   // FP32 filter tile placement (F path)
   const int* ready;     // host-buffer flavour: number of leading pairs whose input has landed in HBM (nullptr: all)
-  int* status;          // [0] = 1 when a CTA gave up waiting for its input
+  int* status;          // [0] = 1 once a CTA gave up waiting for its input, [1] = smallest pair index given up on
+  long long wait_cycles;   // patience of that wait
 };
 
 template <int KIND>  // 0: fundamental matrix, 1: homography
@@ -116,16 +117,20 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
     if (p >= a.n_pairs) break;
     if (a.ready) {
       // The host streams the batch in chunks on a copy stream while this kernel runs and bumps `ready` after each
-      // chunk.  Bounded wait (~4 s): a broken feed must never hang the GPU.
+      // chunk.  The wait is bounded: when copies cannot overlap the kernel (a profiler serialising the streams, a
+      // stalled link) the CTA records the pair, raises the abort flag and retires; the host then runs the pairs from
+      // the smallest recorded index on in a second, ordinary launch.  Nothing can hang.
       __shared__ int s_ok;
       if (threadIdx.x == 0) {
-        const long long t0 = clock64();
-        int ok = 1;
-        while (*reinterpret_cast<const volatile int*>(a.ready) <= p) {
-          __nanosleep(500);
-          if (clock64() - t0 > (1LL << 33)) { ok = 0; break; }
+        int ok = (*reinterpret_cast<volatile int*>(a.status) == 0) ? 1 : 0;
+        if (ok) {
+          const long long t0 = clock64();
+          while (*reinterpret_cast<const volatile int*>(a.ready) <= p) {
+            __nanosleep(500);
+            if (clock64() - t0 > a.wait_cycles || *reinterpret_cast<volatile int*>(a.status) != 0) { ok = 0; break; }
+          }
         }
-        if (!ok) a.status[0] = 1;
+        if (!ok) { atomicMin(a.status + 1, p); atomicExch(a.status, 1); }
         s_ok = ok;
       }
       __syncthreads();
@@ -227,7 +232,7 @@ int ensure_device() {
   CU(cudaEventCreateWithFlags(&g_c.ev_feed, cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&g_c.s_run, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&g_c.s_copy, cudaStreamNonBlocking));
-  CU(cudaMalloc(&g_c.ready, 2 * sizeof(int)));
+  CU(cudaMalloc(&g_c.ready, 4 * sizeof(int)));
   CU(cudaHostAlloc(&g_c.h_ready, kMaxChunks * sizeof(int), cudaHostAllocDefault));
   return 0;
 }
@@ -235,9 +240,10 @@ int ensure_device() {
 template <int KIND>
 int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, double px_th, double conf, int max_iters,
            int metric, int sym_check, int degen, const unsigned long long* d_seeds, double* d_model,
-           unsigned char* d_mask, int* d_stats, cudaStream_t st, const int* d_ready = nullptr, int* d_status = nullptr) {
+           unsigned char* d_mask, int* d_stats, cudaStream_t st, const int* d_ready = nullptr, int* d_status = nullptr,
+           long long wait_cycles = 0) {
   BatchArgs a;
-  a.ready = d_ready; a.status = d_status;
+  a.ready = d_ready; a.status = d_status; a.wait_cycles = wait_cycles;
   a.x1y1 = d1; a.x2y2 = d2; a.n_pairs = n_pairs; a.n = n; a.dim = dim;
   a.px_th = px_th; a.conf = conf; a.laf_coef = 0.0; a.max_iters = max_iters; a.metric = metric;
   a.sym_check = sym_check; a.degen = degen; a.seeds = d_seeds;
@@ -342,13 +348,17 @@ int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim
   int rest = n_pairs - first;
   if (rest <= 0) nchunks = 1;
   const int per = (nchunks > 1) ? (rest + (nchunks - 2)) / (nchunks - 1) : 0;
-  CU(cudaMemsetAsync(g_c.ready, 0, 2 * sizeof(int), cs));
+  static const int k_init[4] = {0, 0, 0x7fffffff, 0};      // ready, abort flag, first pair given up on
+  CU(cudaMemcpyAsync(g_c.ready, k_init, sizeof(k_init), cudaMemcpyHostToDevice, cs));
+  // patience of a waiting CTA: the whole input at a pessimistic 4 GB/s plus 20 ms, in SM cycles (<= 2.1 GHz)
+  const double feed_s = 2.0 * sizeof(double) * (double)n_pairs * (double)pair_elems / 4e9 + 0.020;
+  const long long wait_cycles = (long long)(feed_s * 2.1e9);
   if (seeds) CU(cudaMemcpyAsync(dseed, seeds, sizeof(uint64_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cs));
   CU(cudaEventRecord(g_c.ev_feed, cs));
   CU(cudaStreamWaitEvent(st, g_c.ev_feed, 0));
   CU(cudaEventRecord(g_c.ev0, st));
   rc = launch<KIND>(d1, d2, n_pairs, n, dim, px_th, conf, max_iters, metric, sym_check, degen, seeds ? dseed : nullptr,
-                    dmodel, dmask, dstats, st, g_c.ready, g_c.ready + 1);
+                    dmodel, dmask, dstats, st, g_c.ready, g_c.ready + 1, wait_cycles);
   if (rc) return rc;
   CU(cudaEventRecord(g_c.ev1, st));
   int done = 0;
@@ -366,14 +376,27 @@ int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim
       return fail(DGB200_E_CUDA, "input copy failed", e1 != cudaSuccess ? e1 : e2);
     }
   }
+  int h_status[4] = {0, 0, 0, 0};
+  CU(cudaMemcpyAsync(h_status, g_c.ready, sizeof(h_status), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(cs));
+  CU(cudaStreamSynchronize(st));
+  if (h_status[1] != 0) {
+    // the feed could not overlap the kernel: everything has landed by now, finish the remaining pairs normally
+    int from = h_status[2];
+    if (from < 0) from = 0;
+    if (from < n_pairs) {
+      const size_t off = (size_t)from * pair_elems;
+      rc = launch<KIND>(d1 + off, d2 + off, n_pairs - from, n, dim, px_th, conf, max_iters, metric, sym_check, degen,
+                        seeds ? dseed + from : nullptr, dmodel + (size_t)9 * from, dmask + (size_t)from * n,
+                        dstats + (size_t)4 * from, st);
+      if (rc) return rc;
+      CU(cudaEventRecord(g_c.ev1, st));
+    }
+  }
   CU(cudaMemcpyAsync(model_out, dmodel, sizeof(double) * 9 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(mask_out, dmask, (size_t)n_pairs * n, cudaMemcpyDeviceToHost, st));
   if (stats_out) CU(cudaMemcpyAsync(stats_out, dstats, sizeof(int) * 4 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
-  int h_status[2] = {0, 0};
-  CU(cudaMemcpyAsync(h_status, g_c.ready, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(cs));
   CU(cudaStreamSynchronize(st));
-  if (h_status[1] != 0) return fail(DGB200_E_CUDA, "input feed timed out inside the kernel");
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, g_c.ev0, g_c.ev1));
   g_last_ms = ms;
