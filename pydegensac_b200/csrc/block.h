@@ -212,6 +212,69 @@ DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list)
   return s;
 }
 
+// Two thresholds in one pass over the same row: (SA, listA) = blk_inlidxs(err, thA, listA) and
+// (SB, listB) = blk_inlidxs(err, thB, listB), bit-identical to the two separate calls (same per-thread segments,
+// same summation order), one read of the row and one barrier pair instead of two.  Counts are packed in one int
+// for the scan (N < 65536; larger inputs take the two-call route).
+DG_ENGN void blk_inlidxs2(const Ctx& c, const double* err, double thA, int* listA, Score* SA, double thB, int* listB,
+                          Score* SB) {
+  const int per = (c.N + c.nt - 1) / c.nt;
+  if (per > 8 || c.N >= 65536) {
+    *SA = blk_inlidxs(c, err, thA, listA);
+    *SB = blk_inlidxs(c, err, thB, listB);
+    return;
+  }
+  DG_PROF_BEGIN(21);
+  DG_PROF_COUNT(22, 1);
+  const int beg = c.tid * per;
+  const int end = (beg + per < c.N) ? beg + per : c.N;
+  const double wqA = thA * 9 / 4, wqB = thB * 9 / 4;
+  const double winvA = (thA == 0) ? 0.0 : 1.0 / wqA, winvB = (thB == 0) ? 0.0 : 1.0 / wqB;
+  double e[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = beg + j;
+    e[j] = (i < end) ? ld_row(err + i) : INFINITY;
+  }
+  int cA = 0, cB = 0;
+  double JA = 0.0, JB = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (thA != 0 && !(e[j] >= wqA)) JA += 1 - e[j] * winvA;
+    if (thB != 0 && !(e[j] >= wqB)) JB += 1 - e[j] * winvB;
+    if (e[j] <= thA) ++cA;
+    if (e[j] <= thB) ++cB;
+  }
+  // one scan for both counts, both gains reduced in the same barrier pair
+  const int packed = cA | (cB << 16);
+  const int incl = warp_incl_scan_i(packed, c.lane);
+  const double ja = warp_sum(JA), jb = warp_sum(JB);
+  DG_SYNC();
+  if (c.lane == 31 || c.tid == c.nt - 1) c.sc->red_i[c.wid] = incl;
+  if (c.lane == 0) { c.sc->red_d[c.wid] = ja; c.sc->bc[c.wid] = jb; }
+  DG_SYNC();
+  int base = 0, tot = 0;
+  double jta = 0.0, jtb = 0.0;
+  for (int w = 0; w < c.nw; ++w) {
+    const int t = c.sc->red_i[w];
+    if (w < c.wid) base += t;
+    tot += t;
+    jta += c.sc->red_d[w];
+    jtb += c.sc->bc[w];
+  }
+  const int excl = base + incl - packed;
+  int offA = excl & 0xffff, offB = excl >> 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (e[j] <= thA) listA[offA++] = beg + j;
+    if (e[j] <= thB) listB[offB++] = beg + j;
+  }
+  *SA = make_score(); SA->J = jta; SA->I = (unsigned)(tot & 0xffff);
+  *SB = make_score(); SB->J = jtb; SB->I = (unsigned)(tot >> 16);
+  DG_SYNC();
+  DG_PROF_END(21);
+}
+
 // count of err[i] < th (strict) or <= th over all points
 DG_ENG inline int blk_count_lt(const Ctx& c, const double* err, double th) {
   int cnt = 0;

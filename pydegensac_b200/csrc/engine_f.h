@@ -58,7 +58,14 @@ DG_ENGN Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int* e, in
   #pragma unroll 1
   for (int it = 0; it < kIlsqIters; ++it) {
     blk_resid_w_F(c, P.metric, f, W.err[d], W.w);
-    S = blk_inlidxs(c, W.err[d], th, inl);
+    // The support at the wider threshold is needed on the SAME row unless this iteration improves the score (then
+    // the reference's pointer rotation moves `d` to the previous best row): both lists are built in one pass, the
+    // second one speculatively into a side buffer, and copied over `inl` when it is the one the reference would
+    // have built (the copy keeps `inl` byte-identical to the reference's buffer, whose stale tail is read later by
+    // the caller -- SURVEY App. A).
+    int* spec = W.itmp[0];
+    Score Sspec;
+    blk_inlidxs2(c, W.err[d], th, inl, &S, ths * kMWM, spec, &Sspec);
     if (hash_seen_elsewhere(c, W, ht, inl, (int)S.I, iterID)) return make_score();
     if (score_less(maxS, S)) {
       maxS = S;
@@ -66,8 +73,13 @@ DG_ENGN Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int* e, in
       e[0] = d;
       d = e[1];
       for (int i = 0; i < 9; ++i) Fio[i] = f[i];
+      Ss = blk_inlidxs(c, W.err[d], ths * kMWM, inl);
+    } else {
+      Ss = Sspec;
+      #pragma unroll 1
+      for (int j = c.tid; j < (int)Ss.I; j += c.nt) inl[j] = spec[j];
+      DG_SYNC();
     }
-    Ss = blk_inlidxs(c, W.err[d], ths * kMWM, inl);
     if (Ss.I < 8) return maxS;
     if (8 >= Ss.I) {
       blk_fit_F(c, inl, (int)Ss.I, W.w, f);
