@@ -444,17 +444,15 @@ DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double
     DG_PROF_BEGIN(43);
     #pragma unroll 1
     for (int col = 0; col < 8; ++col) {
-      double mag = used ? -1.0 : fabs(m[0]);
-      if (!(mag == mag)) mag = 1e308 * 10.0;   // NaN -> +inf: wins the search and fails the test below
-      int who = r;
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        const double m2 = __shfl_xor_sync(full, mag, o);
-        const int w2 = __shfl_xor_sync(full, who, o);
-        if (m2 > mag || (m2 == mag && w2 < who)) { mag = m2; who = w2; }
-      }
-      if (!(mag > 0.0) || !(mag < 1e300)) { fast = false; break; }
-      const double inv = 1.0 / shfl_d(m[0], who);
+      // pivot row = an unused row whose |entry| is largest in its upper 32 bits (sign cleared; partial pivoting only
+      // needs a pivot within a factor ~1 of the largest): one REDUX + one ballot instead of a three-stage
+      // shuffle/compare tree.  NaN/Inf keys win and fail the test below.
+      const unsigned key = used ? 0u : ((unsigned)__double2hiint(m[0]) & 0x7fffffffu);
+      const unsigned kmax = __reduce_max_sync(full, key);
+      const int who = (__ffs(__ballot_sync(full, key == kmax)) - 1) & 7;
+      const double pv = shfl_d(m[0], who);
+      if (!(fabs(pv) > 0.0) || !(fabs(pv) < 1e300) || kmax == 0u) { fast = false; break; }
+      const double inv = 1.0 / pv;
       const double fm = m[0];
       const bool piv = (r == who);
 #pragma unroll
