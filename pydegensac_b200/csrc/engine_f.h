@@ -66,6 +66,14 @@ DG_ENGN Score lo_iter_F(const Ctx& c, const FParams& P, Workspace& W, int* e, in
     int* spec = W.itmp[0];
     Score Sspec;
     blk_inlidxs2(c, W.err[d], th, inl, &S, ths * kMWM, spec, &Sspec);
+#if DG_DEVICE_PASS
+    if (!score_less(maxS, S) && Sspec.I > 8 && c.nw >= 2) {
+      // no improvement: the next fit uses the speculative list; run it next to the hash chain (see ffit.h)
+      if (blk_hash_and_fit8_F(c, W, ht, inl, (int)S.I, iterID, spec, (int)Sspec.I, W.w, cur, inl, f)) return make_score();
+      ths -= dth;
+      continue;
+    }
+#endif
     if (hash_seen_elsewhere(c, W, ht, inl, (int)S.I, iterID)) return make_score();
     if (score_less(maxS, S)) {
       maxS = S;

@@ -403,94 +403,95 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
 // rows, the (quirky) weighting, Gauss-Jordan and the rank-2 projection all stay in registers; only the permuted
 // list entries and the 9 results touch memory.
 // ---------------------------------------------------------------------------------------------
+#if DG_DEVICE_PASS
+// Warp section of the fused 8-subset draw + 8-point fit (all 32 lanes of ONE warp): result to c.sc->bc[0..8], success
+// flag to c.sc->bci[1].  COMPACT CODE ON PURPOSE (rolled loops, literal register indices): see DESIGN.md section 7.
+__device__ __noinline__ void warp_sample8_fit(const Ctx& c, int* list, int max_sz, const double* w, uint64_t seed, uint32_t k,
+                                              uint32_t j0) {
+  bool fast = true;
+  const unsigned full = 0xffffffffu;
+  const int lane = c.lane;
+  DG_PROF_BEGIN(41);
+  const int mine = warp_subset_draw(list, max_sz, 8, seed, k, j0, lane);
+  DG_PROF_END(41);
+  DG_PROF_BEGIN(42);
+  // ---- rows: correspondence of row i is list[max_sz - 8 + i] = the value drawn at step 7 - i (held by lane 7 - i)
+  const int r = lane & 7;
+  const int p = __shfl_sync(full, mine, 7 - r);
+  double m[9];
+  f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], m);
+  if (w) {
+    // the reference scales the row-major 9 x 8 array with stride 9 (Ftools.c:431): entry (coefficient t, row i)
+    // sits at 8 t + i and is multiplied by the weight of correspondence (8 t + i) mod 9 when that is < 8
+    const double wi = w[p];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int src = (8 * t + r) % 9;
+      const double wv = __shfl_sync(full, wi, src & 7);
+      if (src < 8) m[t] *= wv;
+    }
+  }
+  // ---- Gauss-Jordan with partial pivoting by role; after every column the row is rotated left, so the pivot
+  //      column is m[0], the right-hand side ends in m[0] after eight steps, zeros are shifted in behind it
+  bool used = false;
+  int mycol = 8;
+  DG_PROF_END(42);
+  DG_PROF_BEGIN(43);
+  #pragma unroll 1
+  for (int col = 0; col < 8; ++col) {
+    // pivot row = an unused row whose |entry| is largest in its upper 32 bits (sign cleared; partial pivoting only
+    // needs a pivot within a factor ~1 of the largest): one REDUX + one ballot instead of a three-stage
+    // shuffle/compare tree.  NaN/Inf keys win and fail the test below.
+    const unsigned key = used ? 0u : ((unsigned)__double2hiint(m[0]) & 0x7fffffffu);
+    const unsigned kmax = __reduce_max_sync(full, key);
+    const int who = (__ffs(__ballot_sync(full, key == kmax)) - 1) & 7;
+    const double pv = shfl_d(m[0], who);
+    if (!(fabs(pv) > 0.0) || !(fabs(pv) < 1e300) || kmax == 0u) { fast = false; break; }
+    const double inv = 1.0 / pv;
+    const double fm = m[0];
+    const bool piv = (r == who);
+#pragma unroll
+    for (int j = 1; j < 9; ++j) {
+      const double pj = shfl_d(m[j], who) * inv;
+      m[j - 1] = piv ? pj : fma(-fm, pj, m[j]);      // eliminate and rotate in one go
+    }
+    m[8] = 0.0;
+    if (piv) { used = true; mycol = col; }
+  }
+  DG_PROF_END(43);
+  DG_PROF_BEGIN(44);
+  if (fast) {
+    double n2 = m[0] * m[0];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) n2 += __shfl_xor_sync(full, n2, o);
+    const double sc = rsqrt(1.0 + n2);
+    WarpScratch* ws = &c.sc->ws[0];
+    __syncwarp();
+    if (lane < 8) ws->cs[mycol] = -m[0] * sc;
+    if (lane == 8) ws->cs[8] = sc;
+    __syncwarp();
+    double n[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) n[i] = ws->cs[i];
+    enforce_rank2_inl(n);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) c.sc->bc[i] = n[i];
+    }
+  }
+  if (lane == 0) c.sc->bci[1] = fast ? 1 : 0;
+  DG_PROF_END(44);
+}
+#endif
+
 DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double* w, DrawCursor& cur, double* f) {
 #if DG_DEVICE_PASS
-  // COMPACT CODE ON PURPOSE.  The first version of this routine unrolled everything (76 KB of straight-line code) and
-  // ran at the instruction-fetch limit (~6 cycles per instruction); here every stage is a short rolled loop whose
-  // register arrays are only ever indexed by literals: the swap log is spread over the lanes, the elimination
-  // rotates its row so that the pivot column is always m[0].
   DG_PROF_BEGIN(7);
   DG_PROF_COUNT(27, 1);
   DG_SYNC();
-  bool fast = true;
-  if (c.wid == 0) {
-    const unsigned full = 0xffffffffu;
-    const int lane = c.lane;
-    DG_PROF_BEGIN(41);
-    const int mine = warp_subset_draw(list, max_sz, 8, cur.seed, cur.k, cur.j, lane);
-    DG_PROF_END(41);
-    DG_PROF_BEGIN(42);
-    // ---- rows: correspondence of row i is list[max_sz - 8 + i] = the value drawn at step 7 - i (held by lane 7 - i)
-    const int r = lane & 7;
-    const int p = __shfl_sync(full, mine, 7 - r);
-    double m[9];
-    f_lin_row(c.x1[p], c.y1[p], c.x2[p], c.y2[p], m);
-    if (w) {
-      // the reference scales the row-major 9 x 8 array with stride 9 (Ftools.c:431): entry (coefficient t, row i)
-      // sits at 8 t + i and is multiplied by the weight of correspondence (8 t + i) mod 9 when that is < 8
-      const double wi = w[p];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int src = (8 * t + r) % 9;
-        const double wv = __shfl_sync(full, wi, src & 7);
-        if (src < 8) m[t] *= wv;
-      }
-    }
-    // ---- Gauss-Jordan with partial pivoting by role; after every column the row is rotated left, so the pivot
-    //      column is m[0], the right-hand side ends in m[0] after eight steps, zeros are shifted in behind it
-    bool used = false;
-    int mycol = 8;
-    DG_PROF_END(42);
-    DG_PROF_BEGIN(43);
-    #pragma unroll 1
-    for (int col = 0; col < 8; ++col) {
-      // pivot row = an unused row whose |entry| is largest in its upper 32 bits (sign cleared; partial pivoting only
-      // needs a pivot within a factor ~1 of the largest): one REDUX + one ballot instead of a three-stage
-      // shuffle/compare tree.  NaN/Inf keys win and fail the test below.
-      const unsigned key = used ? 0u : ((unsigned)__double2hiint(m[0]) & 0x7fffffffu);
-      const unsigned kmax = __reduce_max_sync(full, key);
-      const int who = (__ffs(__ballot_sync(full, key == kmax)) - 1) & 7;
-      const double pv = shfl_d(m[0], who);
-      if (!(fabs(pv) > 0.0) || !(fabs(pv) < 1e300) || kmax == 0u) { fast = false; break; }
-      const double inv = 1.0 / pv;
-      const double fm = m[0];
-      const bool piv = (r == who);
-#pragma unroll
-      for (int j = 1; j < 9; ++j) {
-        const double pj = shfl_d(m[j], who) * inv;
-        m[j - 1] = piv ? pj : fma(-fm, pj, m[j]);      // eliminate and rotate in one go
-      }
-      m[8] = 0.0;
-      if (piv) { used = true; mycol = col; }
-    }
-    DG_PROF_END(43);
-    DG_PROF_BEGIN(44);
-    if (fast) {
-      double n2 = m[0] * m[0];
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) n2 += __shfl_xor_sync(full, n2, o);
-      const double sc = rsqrt(1.0 + n2);
-      WarpScratch* ws = &c.sc->ws[0];
-      __syncwarp();
-      if (lane < 8) ws->cs[mycol] = -m[0] * sc;
-      if (lane == 8) ws->cs[8] = sc;
-      __syncwarp();
-      double n[9];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) n[i] = ws->cs[i];
-      enforce_rank2_inl(n);
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) c.sc->bc[i] = n[i];
-      }
-    }
-    if (lane == 0) c.sc->bci[1] = fast ? 1 : 0;
-    DG_PROF_END(44);
-  }
-  DG_PROF_BEGIN(45);
+  if (c.wid == 0) warp_sample8_fit(c, list, max_sz, w, cur.seed, cur.k, cur.j);
   DG_SYNC();
-  DG_PROF_END(45);
-  fast = c.sc->bci[1] != 0;
+  const bool fast = c.sc->bci[1] != 0;
   cur.j += 8u;
   if (fast) {
 #pragma unroll
@@ -511,50 +512,55 @@ DG_ENGN void blk_sample8_fit_F(const Ctx& c, int* list, int max_sz, const double
 // The reference de-duplicates LO inlier sets with SuperFastHash + a 64-bucket chained table
 // (hash.c:49-96, exp_ranF.c:675-686).  Only "(hash,len) seen under this iterID / another iterID /
 // never" matters, so a flat list is equivalent.  Returns true when the refinement must abort.
+#if DG_DEVICE_PASS
+// Warp section of the de-duplication (all 32 lanes of ONE warp): the list is fetched 32 words at a time (coalesced,
+// next block in flight while the current one is hashed), every lane runs the same serial SuperFastHash chain on words
+// handed round by shuffles, and the table scan is spread over the lanes.  Verdict to c.sc->bci[0]
+// (0: inserted, 1: already ours, 2: abort).
+__device__ __noinline__ void warp_hash_verdict(const Ctx& c, Workspace& W, int htn, const int* list, int n, int iterID) {
+  const unsigned full = 0xffffffffu;
+  uint32_t h = 0u;
+  if (n > 0) {
+    h = sfh_init(n);
+    uint32_t v = (c.lane < n) ? (uint32_t)list[c.lane] : 0u;
+    #pragma unroll 1
+    for (int base = 0; base < n; base += 32) {
+      const int nxt = base + 32 + c.lane;
+      const uint32_t vn = (nxt < n) ? (uint32_t)list[nxt] : 0u;
+      if (n - base >= 32) {
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) h = sfh_word(h, __shfl_sync(full, v, j));
+      } else {
+        #pragma unroll 1
+        for (int j = 0; j < n - base; ++j) h = sfh_word(h, __shfl_sync(full, v, j));
+      }
+      v = vn;
+    }
+    h = sfh_final(h);
+  }
+  bool same = false, other = false;
+  #pragma unroll 1
+  for (int i = c.lane; i < htn; i += 32) {
+    if (W.hhash[i] == h && W.hlen[i] == n) {
+      if (W.hid[i] == iterID) same = true; else other = true;
+    }
+  }
+  same = __any_sync(full, same);
+  other = __any_sync(full, other);
+  int verdict = 0;
+  if (same) verdict = 1; else if (other) verdict = 2;
+  if (c.lane == 0) {
+    if (verdict == 0 && htn < W.hcap) { W.hhash[htn] = h; W.hlen[htn] = n; W.hid[htn] = iterID; }
+    c.sc->bci[0] = verdict;
+  }
+}
+#endif
+
 DG_ENGN bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, const int* list, int n, int iterID) {
   DG_PROF_BEGIN(4);
   DG_SYNC();
 #if DG_DEVICE_PASS
-  // Warp 0: the list is fetched 32 words at a time (coalesced, next block in flight while the current one is
-  // hashed), every lane runs the same serial SuperFastHash chain on words handed round by shuffles, and the table
-  // scan is spread over the lanes.  The chain itself cannot be parallelised; this removes the memory latency from it.
-  if (c.wid == 0) {
-    const unsigned full = 0xffffffffu;
-    uint32_t h = 0u;
-    if (n > 0) {
-      h = sfh_init(n);
-      uint32_t v = (c.lane < n) ? (uint32_t)list[c.lane] : 0u;
-      #pragma unroll 1
-      for (int base = 0; base < n; base += 32) {
-        const int nxt = base + 32 + c.lane;
-        const uint32_t vn = (nxt < n) ? (uint32_t)list[nxt] : 0u;
-        if (n - base >= 32) {
-#pragma unroll 4
-          for (int j = 0; j < 32; ++j) h = sfh_word(h, __shfl_sync(full, v, j));
-        } else {
-          #pragma unroll 1
-          for (int j = 0; j < n - base; ++j) h = sfh_word(h, __shfl_sync(full, v, j));
-        }
-        v = vn;
-      }
-      h = sfh_final(h);
-    }
-    bool same = false, other = false;
-    #pragma unroll 1
-    for (int i = c.lane; i < ht.n; i += 32) {
-      if (W.hhash[i] == h && W.hlen[i] == n) {
-        if (W.hid[i] == iterID) same = true; else other = true;
-      }
-    }
-    same = __any_sync(full, same);
-    other = __any_sync(full, other);
-    int verdict = 0;  // 0: insert, 1: already ours, 2: abort
-    if (same) verdict = 1; else if (other) verdict = 2;
-    if (c.lane == 0) {
-      if (verdict == 0 && ht.n < W.hcap) { W.hhash[ht.n] = h; W.hlen[ht.n] = n; W.hid[ht.n] = iterID; }
-      c.sc->bci[0] = verdict;
-    }
-  }
+  if (c.wid == 0) warp_hash_verdict(c, W, ht.n, list, n, iterID);
 #else
   if (c.tid == 0) {
     const uint32_t h = superfasthash_i32(list, n);
@@ -578,5 +584,39 @@ DG_ENGN bool hash_seen_elsewhere(const Ctx& c, Workspace& W, HashTab& ht, const 
   DG_PROF_END(4);
   return verdict == 2;
 }
+
+#if DG_DEVICE_PASS
+// De-duplication of list A and the speculative 8-point fit on the wide list B (a private copy in `spec`) side by side
+// on two warps: the serial hash chain (warp 1) and the fit (warp 0) are independent until the verdict is known.
+// Abort: true is returned, nothing is committed (`inl`, the draw cursor and f are untouched -- exactly the
+// reference's state when it returns after the hash).  Otherwise the permuted list is copied into `inl` (byte-for-byte
+// what the reference's in-place randsubset leaves there), the cursor advances by the eight draws and f holds the fit.
+DG_ENGN bool blk_hash_and_fit8_F(const Ctx& c, Workspace& W, HashTab& ht, const int* listA, int nA, int iterID, int* spec,
+                                 int nB, const double* w, DrawCursor& cur, int* inl, double* f) {
+  DG_SYNC();
+  if (c.wid == 1) warp_hash_verdict(c, W, ht.n, listA, nA, iterID);
+  if (c.wid == 0) warp_sample8_fit(c, spec, nB, w, cur.seed, cur.k, cur.j);
+  DG_SYNC();
+  const int verdict = c.sc->bci[0];
+  const bool fast = c.sc->bci[1] != 0;
+  double r[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r[i] = c.sc->bc[i];
+  DG_SYNC();
+  if (verdict == 0 && ht.n < W.hcap) ++ht.n;
+  if (verdict == 2) return true;
+  #pragma unroll 1
+  for (int j = c.tid; j < nB; j += c.nt) inl[j] = spec[j];
+  cur.j += 8u;
+  DG_SYNC();
+  if (fast) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = r[i];
+  } else {
+    blk_fit_F(c, inl + nB - 8, 8, w, f);   // rank-deficient sample: Householder route on the permuted list
+  }
+  return false;
+}
+#endif
 
 }  // namespace dg
