@@ -328,7 +328,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=8192)
+    ap.add_argument("--pairs-per-gpu", type=int, default=16384)
     ap.add_argument("--cpu-pairs-per-core", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
