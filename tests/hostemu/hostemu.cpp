@@ -94,6 +94,8 @@ extern "C" uint32_t emu_hash(const int* idx, int n) { return superfasthash_i32(i
 extern "C" int emu_nsamples(int a, int b, int c, double d) { return nsamples(a, b, c, d); }
 extern "C" void emu_min_eigvec9(double* C, double* v) { min_eigvec9(C, v); }
 extern "C" void emu_enforce_rank2(double* F) { enforce_rank2(F); }
+extern "C" void emu_enforce_rank2_slow(double* F) { enforce_rank2_slow(F); }
+extern "C" int emu_smallest_right_sv3_fast(const double* F, double* v) { return smallest_right_sv3_fast(F, v) ? 1 : 0; }
 extern "C" void emu_left_null(double* Z, int len, double* q) { left_null_9xk(Z, len, q); }
 extern "C" void emu_minimal_sample(uint64_t seed, uint32_t k, int N, int m, int* sel) {
   if (m == 7) minimal_sample<7>(seed, k, N, sel); else minimal_sample<4>(seed, k, N, sel);
