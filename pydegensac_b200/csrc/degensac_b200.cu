@@ -352,7 +352,8 @@ int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim
   CU(cudaMemcpyAsync(g_c.ready, k_init, sizeof(k_init), cudaMemcpyHostToDevice, cs));
   // patience of a waiting CTA: the whole input at a pessimistic 4 GB/s plus 20 ms, in SM cycles (<= 2.1 GHz)
   const double feed_s = 2.0 * sizeof(double) * (double)n_pairs * (double)pair_elems / 4e9 + 0.020;
-  const long long wait_cycles = (long long)(feed_s * 2.1e9);
+  long long wait_cycles = (long long)(feed_s * 2.1e9);
+  if (const char* e = getenv("DGB200_FEED_WAIT_US")) wait_cycles = (long long)(atof(e) * 2.1e3);   // tests: force the fallback
   if (seeds) CU(cudaMemcpyAsync(dseed, seeds, sizeof(uint64_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cs));
   CU(cudaEventRecord(g_c.ev_feed, cs));
   CU(cudaStreamWaitEvent(st, g_c.ev_feed, 0));

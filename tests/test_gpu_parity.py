@@ -132,3 +132,26 @@ def test_python_api_on_gpu():
     z = np.ones((20, 2))
     Fz, mz = pdg.findFundamentalMatrix(z, z, 1.0, 0.99, 100, seed=1)
     assert np.abs(Fz).sum() == 0 and not any(mz)
+
+
+def test_host_feed_fallback_gives_identical_results():
+    """The host-buffer API streams its input while the kernel runs; CTAs that outwait their patience retire and a
+    second launch finishes the batch (what happens when a profiler serialises the streams).  Forcing that path
+    (DGB200_FEED_WAIT_US=0, read per call) must not change a single output byte.  The batch is large enough for the
+    chunked feed (several chunks beyond the first 592 pairs)."""
+    import os
+    from pydegensac_b200 import _cabi
+    P = 1500
+    b1, b2 = batch_F(8, 600, 0.5, seed0=900)
+    b1 = np.ascontiguousarray(np.tile(b1, (P // 8 + 1, 1, 1))[:P]); b2 = np.ascontiguousarray(np.tile(b2, (P // 8 + 1, 1, 1))[:P])
+    seeds = np.arange(P, dtype=np.uint64) % 8
+    a = _cabi.fundamental_batch(b1, b2, 1.0, 0.99, 300, 0, True, 0.0, True, seeds)
+    os.environ["DGB200_FEED_WAIT_US"] = "0"
+    try:
+        b = _cabi.fundamental_batch(b1, b2, 1.0, 0.99, 300, 0, True, 0.0, True, seeds)
+    finally:
+        del os.environ["DGB200_FEED_WAIT_US"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    # identical scenes with identical seeds give identical rows (batch-order independence of the persistent CTAs)
+    for i in range(8, P):
+        assert np.array_equal(a[1][i], a[1][i % 8])
