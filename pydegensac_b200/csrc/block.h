@@ -35,6 +35,9 @@ struct Ctx {
   const double* x1; const double* y1; const double* x2; const double* y2;   // SoA correspondences
   BlockScratch* sc;
   const Tile32* t32;   // FP32 upper-bound filter tile (nullptr: the wave scores in FP64)
+  // LAF helper correspondences (laf_coef > 0, [N,6] input): p1 = x + (a12, a22), p2 = x + (a11, a21) in each image
+  // (bindings.cpp:337-389); rows {p1: x1,y1,x2,y2, p2: x1,y1,x2,y2}, nullptr when the gate is off
+  const double* laf[8];
 };
 
 #if DG_DEVICE_PASS

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
   c.x1 = soa; c.y1 = soa + row; c.x2 = soa + 2 * row; c.y2 = soa + 3 * row;
   c.sc = sc;
   c.t32 = nullptr;
+  const bool use_laf = (a.laf_coef > 0) && (a.dim == 6);
+  for (int i = 0; i < 8; ++i) c.laf[i] = use_laf ? W.laf[i] : nullptr;
 
   for (;;) {
     __syncthreads();
@@ -148,8 +150,14 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
       }
     } else {
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        soa[i] = g1[(size_t)i * a.dim]; soa[row + i] = g1[(size_t)i * a.dim + 1];
-        soa[2 * row + i] = g2[(size_t)i * a.dim]; soa[3 * row + i] = g2[(size_t)i * a.dim + 1];
+        const double* q1 = g1 + (size_t)i * a.dim;
+        const double* q2 = g2 + (size_t)i * a.dim;
+        soa[i] = q1[0]; soa[row + i] = q1[1];
+        soa[2 * row + i] = q2[0]; soa[3 * row + i] = q2[1];
+        if (use_laf) {   // columns (x, y, a11, a12, a21, a22): p1 = x + (a12, a22), p2 = x + (a11, a21) (bindings.cpp:355-385)
+          W.laf[0][i] = q1[0] + q1[3]; W.laf[1][i] = q1[1] + q1[5]; W.laf[2][i] = q2[0] + q2[3]; W.laf[3][i] = q2[1] + q2[5];
+          W.laf[4][i] = q1[0] + q1[2]; W.laf[5][i] = q1[1] + q1[4]; W.laf[6][i] = q2[0] + q2[2]; W.laf[7][i] = q2[1] + q2[4];
+        }
       }
     }
     __syncthreads();
@@ -163,7 +171,8 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
       c.t32 = &t32;
       dg::FParams P;
       dg::f_thresholds(a.px_th, a.sym_check, &P.th, &P.sym_th);
-      P.conf = a.conf; P.laf_coef = 0.0; P.max_iters = a.max_iters; P.metric = a.metric; P.degen = a.degen;
+      P.conf = a.conf; P.laf_coef = a.laf_coef; P.max_iters = a.max_iters; P.metric = a.metric; P.degen = a.degen;
+      P.do_laf = use_laf ? 1 : 0; P.th_laf = a.laf_coef * P.th;
       P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = a.chunk;
       dg::ransac_F_pair(c, P, W, model, mask, s_stats);
     } else {
@@ -241,11 +250,11 @@ template <int KIND>
 int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, double px_th, double conf, int max_iters,
            int metric, int sym_check, int degen, const unsigned long long* d_seeds, double* d_model,
            unsigned char* d_mask, int* d_stats, cudaStream_t st, const int* d_ready = nullptr, int* d_status = nullptr,
-           long long wait_cycles = 0) {
+           long long wait_cycles = 0, double laf_coef = 0.0) {
   BatchArgs a;
   a.ready = d_ready; a.status = d_status; a.wait_cycles = wait_cycles;
   a.x1y1 = d1; a.x2y2 = d2; a.n_pairs = n_pairs; a.n = n; a.dim = dim;
-  a.px_th = px_th; a.conf = conf; a.laf_coef = 0.0; a.max_iters = max_iters; a.metric = metric;
+  a.px_th = px_th; a.conf = conf; a.laf_coef = laf_coef; a.max_iters = max_iters; a.metric = metric;
   a.sym_check = sym_check; a.degen = degen; a.seeds = d_seeds;
   a.model_out = d_model; a.mask_out = d_mask; a.stats_out = d_stats;
   a.chunk = kChunk;
@@ -305,7 +314,8 @@ int check_args(int kind, const void* p1, const void* p2, int n_pairs, int n, int
   if (kind == 1 && n < 4) return fail(DGB200_E_ARG, "x1y1 should be an array with dims [n,2], n>=4");
   if (kind == 0 && (metric < 0 || metric > 1)) return fail(DGB200_E_METRIC, "unknown fundamental-matrix error_type");
   if (kind == 1 && (metric < 0 || metric > 4)) return fail(DGB200_E_METRIC, "unknown homography error_type");
-  if (laf_coef > 0) return fail(DGB200_E_UNSUPPORTED, "laf_coef > 0 (LAF consistency gate) is not implemented yet");
+  if (laf_coef > 0 && dim != 6) return fail(DGB200_E_ARG, "laf_coef > 0 needs [n,6] inputs (x, y, a11, a12, a21, a22)");
+  if (laf_coef > 0 && kind == 1) return fail(DGB200_E_UNSUPPORTED, "laf_coef > 0 (LAF consistency gate) is not implemented for homographies yet");
   return 0;
 }
 
@@ -359,7 +369,7 @@ int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim
   CU(cudaStreamWaitEvent(st, g_c.ev_feed, 0));
   CU(cudaEventRecord(g_c.ev0, st));
   rc = launch<KIND>(d1, d2, n_pairs, n, dim, px_th, conf, max_iters, metric, sym_check, degen, seeds ? dseed : nullptr,
-                    dmodel, dmask, dstats, st, g_c.ready, g_c.ready + 1, wait_cycles);
+                    dmodel, dmask, dstats, st, g_c.ready, g_c.ready + 1, wait_cycles, laf_coef);
   if (rc) return rc;
   CU(cudaEventRecord(g_c.ev1, st));
   int done = 0;
@@ -389,7 +399,7 @@ int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim
       const size_t off = (size_t)from * pair_elems;
       rc = launch<KIND>(d1 + off, d2 + off, n_pairs - from, n, dim, px_th, conf, max_iters, metric, sym_check, degen,
                         seeds ? dseed + from : nullptr, dmodel + (size_t)9 * from, dmask + (size_t)from * n,
-                        dstats + (size_t)4 * from, st);
+                        dstats + (size_t)4 * from, st, nullptr, nullptr, 0, laf_coef);
       if (rc) return rc;
       CU(cudaEventRecord(g_c.ev1, st));
     }
@@ -414,7 +424,8 @@ int run_dev(const double* d1, const double* d2, int n_pairs, int n, int dim, dou
   rc = ensure_device();
   if (rc) return rc;
   return launch<KIND>(d1, d2, n_pairs, n, dim, px_th, conf, max_iters, metric, sym_check, degen,
-                      (const unsigned long long*)d_seeds, d_model, d_mask, d_stats, (cudaStream_t)stream);
+                      (const unsigned long long*)d_seeds, d_model, d_mask, d_stats, (cudaStream_t)stream, nullptr, nullptr, 0,
+                      laf_coef);
 }
 
 }  // namespace

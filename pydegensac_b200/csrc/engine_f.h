@@ -170,6 +170,10 @@ DG_ENGN bool run_lo_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, 
       S.Is = blk_sym_count_F(c, f, W.inliers, (int)S.I, P.sym_th);
       if (S.Is < st.maxS.Is) do_update = false;
     }
+    if (P.do_laf && do_update) {   // exp_ranF.c:1536-1555 / 1664-1683
+      S.Ilafs = blk_laf_count_F(c, P.metric, f, W.inliers, (int)S.I, P.th_laf);
+      if (S.Ilafs < st.maxS.Ilafs) do_update = false;
+    }
     if (do_update) {
       const int t = st.e[0]; st.e[0] = st.e[3]; st.e[3] = t;
       st.maxS = S;
@@ -515,6 +519,10 @@ DG_ENGN void replay_iteration_F(const Ctx& c, const FParams& P, Workspace& W, FS
       if (P.do_sym) {
         S.Is = blk_sym_count_F(c, f, W.inliers, (int)S.I, P.sym_th);
         if (S.Is < st.maxS.Is) ok = false;
+      }
+      if (ok && P.do_laf) {   // LAF gate (exp_ranF.c:1394-1412)
+        S.Ilafs = blk_laf_count_F(c, P.metric, f, W.inliers, (int)S.I, P.th_laf);
+        if (S.Ilafs < st.maxS.Ilafs) ok = false;
       }
       if (!ok) continue;  // the reference `continue`s: the best-sample test below is skipped too
       st.e[i] = st.e[3];

@@ -20,6 +20,7 @@ struct Workspace {
   double* errBest;  // errorsBest
   double* w;        // LSQ weights
   double* dtmp[8];  // scratch rows (DEGENSAC / H paths)
+  double* laf[8];   // LAF helper correspondences (see Ctx::laf)
   int* inliers;
   int* intbuff;
   int* intbuff_best;
@@ -39,6 +40,8 @@ struct HashTab { int n; };
 
 struct FParams {
   double th, sym_th, conf, laf_coef;
+  double th_laf;    // laf_coef * th (exp_ranF.c:1272)
+  int do_laf;       // DO_LAF_CHECK (exp_ranF.c:1271)
   int max_iters, metric, degen, do_sym;
   uint64_t seed;
   int chunk;
@@ -145,6 +148,21 @@ __device__ __noinline__ int warp_subset_draw(int* list, int max_sz, int siz, uin
   return mine;
 }
 #endif
+
+// LAF-consistency count over an index list (gates at exp_ranF.c:1394-1412, 1536-1555, 1664-1683): residual of the two
+// helper correspondences under F with the run's own metric (FDS1idx), Ilafs = min(#p2 passing, #p1 passing).
+DG_ENGN unsigned blk_laf_count_F(const Ctx& c, int metric, const double* F, const int* list, int n, double th_laf) {
+  int c1 = 0, c2 = 0;
+  #pragma unroll 1
+  for (int j = c.tid; j < n; j += c.nt) {
+    const int i = list[j];
+    if (f_resid(metric, F, c.laf[0][i], c.laf[1][i], c.laf[2][i], c.laf[3][i]) <= th_laf) ++c1;
+    if (f_resid(metric, F, c.laf[4][i], c.laf[5][i], c.laf[6][i], c.laf[7][i]) <= th_laf) ++c2;
+  }
+  const unsigned p1 = (unsigned)blk_sum_i(c, c1);
+  const unsigned p2 = (unsigned)blk_sum_i(c, c2);
+  return p2 < p1 ? p2 : p1;
+}
 
 // Partial Fisher-Yates permutation of list[0..max_sz) drawing `siz` slots; the subset is the last
 // `siz` entries (reference randsubset, rtools.c:25-39).

@@ -14,7 +14,7 @@ DG_HD size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 DG_HD size_t workspace_bytes(int N, int chunk) {
   size_t b = 0;
-  b += align_up(sizeof(double) * (size_t)N, 128) * 14;            // err[4], errBest, w, dtmp[8]
+  b += align_up(sizeof(double) * (size_t)N, 128) * 22;            // err[4], errBest, w, dtmp[8], laf[8]
   b += align_up(sizeof(int) * (size_t)(N + kListPad), 128) * 7;   // inliers, intbuff, intbuff_best, itmp[4]
   b += align_up((size_t)N, 128) * 4;                              // btmp[4]
   b += align_up(sizeof(Cand) * (size_t)(3 * chunk), 128);         // hypothesis queue
@@ -37,6 +37,8 @@ DG_HD void workspace_carve(unsigned char* base, int N, int chunk, Workspace* W, 
   W->w = (double*)p; p += rowd;
   #pragma unroll 1
   for (int i = 0; i < 8; ++i) { W->dtmp[i] = (double*)p; p += rowd; }
+  #pragma unroll 1
+  for (int i = 0; i < 8; ++i) { W->laf[i] = (double*)p; p += rowd; }
   W->inliers = (int*)p; p += rowi;
   W->intbuff = (int*)p; p += rowi;
   W->intbuff_best = (int*)p; p += rowi;

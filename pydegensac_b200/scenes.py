@@ -73,3 +73,14 @@ def batch_F(n_pairs, n=2000, inlier_ratio=0.30, seed0=0, plane_frac=0.0):
         a, b, _ = scene_F(n, inlier_ratio, seed0 + s, plane_frac)
         p1[s], p2[s] = a, b
     return p1, p2
+
+
+def scene_F_laf(n=600, inlier_ratio=0.5, seed=0, jitter=0.6, plane_frac=0.0):
+    """scene_F plus local affine frames: [N,6] rows (x, y, a11, a12, a21, a22) for the LAF-consistency gate.
+    Shapes are ~6 px, equal up to `jitter` px between the two images on inliers, unrelated on outliers."""
+    p1, p2, gt = scene_F(n, inlier_ratio, seed, plane_frac)
+    rng = np.random.default_rng(seed + 1000)
+    A1 = np.tile(np.array([6.0, 0.0, 0.0, 6.0]), (n, 1)) + rng.normal(0, 1.0, (n, 4))
+    A2 = A1 + rng.normal(0, jitter, (n, 4))
+    A2[~gt] = rng.normal(0, 6, ((~gt).sum(), 4))
+    return np.hstack([p1, A1]), np.hstack([p2, A2]), gt

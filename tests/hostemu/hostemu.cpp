@@ -46,6 +46,15 @@ static void emu_setup(Emu& E, const double* x1y1, const double* x2y2, int n, int
   E.c.x1 = x1; E.c.y1 = y1; E.c.x2 = x2; E.c.y2 = y2;
   E.c.sc = &E.sc;
   E.c.t32 = nullptr;
+  for (int k = 0; k < 8; ++k) E.c.laf[k] = nullptr;
+  if (dim == 6) {
+    for (int i = 0; i < n; ++i) {
+      const double* q1 = x1y1 + (size_t)6 * i; const double* q2 = x2y2 + (size_t)6 * i;
+      E.W.laf[0][i] = q1[0] + q1[3]; E.W.laf[1][i] = q1[1] + q1[5]; E.W.laf[2][i] = q2[0] + q2[3]; E.W.laf[3][i] = q2[1] + q2[5];
+      E.W.laf[4][i] = q1[0] + q1[2]; E.W.laf[5][i] = q1[1] + q1[4]; E.W.laf[6][i] = q2[0] + q2[2]; E.W.laf[7][i] = q2[1] + q2[4];
+    }
+    for (int k = 0; k < 8; ++k) E.c.laf[k] = E.W.laf[k];
+  }
   E.tile = (Pt32*)malloc(sizeof(Pt32) * (size_t)n);
 }
 
@@ -53,12 +62,13 @@ extern "C" int emu_find_fundamental(const double* x1y1, const double* x2y2, int 
                                     int max_iters, int error_type, int sym_check, double laf_coef, int degen,
                                     uint64_t seed, int chunk, double* F, unsigned char* mask, int* stats) {
   if (n < 8 || (dim != 2 && dim != 6)) return -1;
-  if (laf_coef > 0) return -3;
+  if (laf_coef > 0 && dim != 6) return -1;
   Emu E;
   emu_setup(E, x1y1, x2y2, n, dim, chunk);
   FParams P;
   f_thresholds(px_th, sym_check, &P.th, &P.sym_th);
-  P.conf = conf; P.laf_coef = 0; P.max_iters = max_iters; P.metric = error_type; P.degen = degen;
+  P.conf = conf; P.laf_coef = laf_coef; P.max_iters = max_iters; P.metric = error_type; P.degen = degen;
+  P.do_laf = laf_coef > 0 ? 1 : 0; P.th_laf = laf_coef * P.th;
   P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk;
   if (g_use_filter32) { blk_prepare_tile32(E.c, E.tile, &E.t32); E.c.t32 = &E.t32; }
   ransac_F_pair(E.c, P, E.W, F, mask, stats);

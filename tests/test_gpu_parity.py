@@ -155,3 +155,26 @@ def test_host_feed_fallback_gives_identical_results():
     # identical scenes with identical seeds give identical rows (batch-order independence of the persistent CTAs)
     for i in range(8, P):
         assert np.array_equal(a[1][i], a[1][i % 8])
+
+
+def test_F_laf_gate_vs_reference_on_gpu(ref_oracle):
+    """LAF-consistency gate through the C ABI ([N,6] inputs, laf_coef > 0) against the compiled reference."""
+    from pydegensac_b200 import _cabi
+    from pydegensac_b200.scenes import scene_F_laf
+    rng = np.random.default_rng(5)
+    checked = 0
+    for case in range(36):
+        n = int(rng.choice([100, 300, 600, 1000])); ratio = float(rng.choice([0.4, 0.6, 0.8])); seed = int(rng.integers(1 << 20))
+        jitter = float(rng.choice([0.2, 0.6, 1.5])); laf = float(rng.choice([0.5, 1.0, 2.0, 5.0])); et = int(rng.integers(2))
+        sym = bool(rng.integers(2)); mi = int(rng.choice([200, 1000, 3000])); plane = float(rng.choice([0, 0, 0.6]))
+        x1, x2, _ = scene_F_laf(n, ratio, seed, jitter, plane)
+        a = ref_oracle.find_fundamental(x1, x2, 1.0, 0.999, mi, error_type=et, sym_check=sym, laf_coef=laf, degen_check=True, seed=seed)
+        if a[2][3] <= 4 or a[2][2] >= a[2][0]:
+            continue
+        F, m, s = _cabi.fundamental_batch(x1, x2, 1.0, 0.999, mi, et, sym, laf, True, [seed])
+        _cmp(a, (F[0], m[0], s[0]), "F LAF case %d" % case)
+        checked += 1
+    assert checked >= 25
+    # [N,2] inputs with laf_coef > 0 are rejected at the C ABI (the Python layer warns and drops the coefficient)
+    with pytest.raises(Exception):
+        _cabi.fundamental_batch(x1[:, :2].copy(), x2[:, :2].copy(), 1.0, 0.999, 100, 0, True, 1.0, True, [1])
