@@ -37,7 +37,7 @@ extern "C" {
 #define DGB200_OK 0
 #define DGB200_E_ARG (-1)          /* bad shape: n < 8 (F) / n < 4 (H), dim not 2 or 6 (bindings.cpp:32-47, 267-282) */
 #define DGB200_E_METRIC (-2)       /* unknown error_type (bindings.cpp:10-17) */
-#define DGB200_E_UNSUPPORTED (-3)  /* laf_coef > 0 on the homography entry points: gate built for F only so far */
+#define DGB200_E_UNSUPPORTED (-3)  /* reserved (the LAF-consistency gate, SURVEY.md §8(f).1, is implemented for [n,6] inputs) */
 #define DGB200_E_CUDA (-10)        /* no device / CUDA runtime failure: the engine has no CPU fallback */
 
 /* error_type numbering of the reference (bindings.cpp:10-17) */

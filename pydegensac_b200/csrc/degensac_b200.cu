@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
     } else {
       dg::HParams P;
       dg::h_thresholds(a.metric, a.px_th, a.sym_check, &P.th, &P.sym_th);
-      P.conf = a.conf; P.laf_coef = 0.0; P.max_iters = a.max_iters; P.metric = a.metric;
+      P.conf = a.conf; P.laf_coef = a.laf_coef; P.max_iters = a.max_iters; P.metric = a.metric;
+      P.do_laf = use_laf ? 1 : 0; P.th_laf = a.laf_coef * P.th;
       P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = a.chunk;
       dg::ransac_H_pair(c, P, W, model, mask, s_stats);
     }
@@ -315,7 +316,6 @@ int check_args(int kind, const void* p1, const void* p2, int n_pairs, int n, int
   if (kind == 0 && (metric < 0 || metric > 1)) return fail(DGB200_E_METRIC, "unknown fundamental-matrix error_type");
   if (kind == 1 && (metric < 0 || metric > 4)) return fail(DGB200_E_METRIC, "unknown homography error_type");
   if (laf_coef > 0 && dim != 6) return fail(DGB200_E_ARG, "laf_coef > 0 needs [n,6] inputs (x, y, a11, a12, a21, a22)");
-  if (laf_coef > 0 && kind == 1) return fail(DGB200_E_UNSUPPORTED, "laf_coef > 0 (LAF consistency gate) is not implemented for homographies yet");
   return 0;
 }
 

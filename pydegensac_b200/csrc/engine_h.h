@@ -20,6 +20,8 @@ namespace dg {
 
 struct HParams {
   double th, sym_th, conf, laf_coef;
+  double th_laf;    // laf_coef * th (exp_ranH.c:500)
+  int do_laf;       // DO_LAF_CHECK (exp_ranH.c:499)
   int max_iters, metric, do_sym;
   uint64_t seed;
   int chunk;
@@ -51,6 +53,20 @@ DG_ENGN unsigned blk_sym_count_H(const Ctx& c, const double* h, const int* list,
     if (h_resid_symmax_gate(s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]) <= sym_th) ++cnt;
   }
   return (unsigned)blk_sum_i(c, cnt);
+}
+
+// LAF helper counts over a list: how many entries pass laf threshold for helper pair `which` (0: p1, 1: p2)
+DG_ENGN int blk_laf_count_H(const Ctx& c, int metric, const double* h, const int* list, int n, double th_laf, int which) {
+  HSym s;
+  if (metric != H_SAMPSON) h_sym_prepare(h, &s);
+  const double* const* L = c.laf + 4 * which;
+  int cnt = 0;
+  #pragma unroll 1
+  for (int j = c.tid; j < n; j += c.nt) {
+    const int i = list[j];
+    if (h_resid_laf(metric, h, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i], L[0][i], L[1][i], L[2][i], L[3][i]) <= th_laf) ++cnt;
+  }
+  return blk_sum_i(c, cnt);
 }
 
 // hash de-duplication: same table and routine as the F engine (ffit.h)
@@ -138,6 +154,7 @@ struct HState {
   int e[5];
   double H[9];
   int max_sam, iter_cnt, iterID, no_rej;
+  int p1_acc;   // the reference's `p1_inliers`: never reset, it accumulates over every LAF gate of the run (exp_ranH.c:501)
   HashTab ht;
   DrawCursor cur;
 };
@@ -165,6 +182,13 @@ DG_ENGN bool run_lo_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, 
       const Score Sc = blk_inlidxs(c, W.err[d], P.th, W.itmp[0]);
       S.Is = blk_sym_count_H(c, h, W.itmp[0], (int)Sc.I, P.sym_th);
       if (S.Is < st.maxS.Is) do_update = false;
+    }
+    if (do_update && P.do_laf) {   // exp_ranH.c:718-736 / 834-849 (no early exit on the first helper here)
+      const Score Sc = blk_inlidxs(c, W.err[d], P.th, W.itmp[0]);
+      st.p1_acc += blk_laf_count_H(c, P.metric, h, W.itmp[0], (int)Sc.I, P.th_laf, 0);
+      const unsigned c2 = (unsigned)blk_laf_count_H(c, P.metric, h, W.itmp[0], (int)Sc.I, P.th_laf, 1);
+      S.Ilafs = c2 < (unsigned)st.p1_acc ? c2 : (unsigned)st.p1_acc;
+      if (S.Ilafs < st.maxS.Ilafs) do_update = false;
     }
     if (do_update) {
       const int t = st.e[0]; st.e[0] = st.e[3]; st.e[3] = t;
@@ -272,6 +296,13 @@ DG_ENGN void replay_iteration_H(const Ctx& c, const HParams& P, Workspace& W, HS
       S.Is = blk_sym_count_H(c, h, W.itmp[0], (int)S.I, P.sym_th);
       if (S.Is < st.maxS.Is) return;  // `continue`: skips LO scheduling and the termination update
     }
+    if (P.do_laf) {   // exp_ranH.c:600-619; the list is the current row's inliers (same as S's list)
+      st.p1_acc += blk_laf_count_H(c, P.metric, h, W.itmp[0], (int)S.I, P.th_laf, 0);
+      if ((unsigned)st.p1_acc < st.maxS.Ilafs) return;
+      const unsigned c2 = (unsigned)blk_laf_count_H(c, P.metric, h, W.itmp[0], (int)S.I, P.th_laf, 1);
+      S.Ilafs = c2 < (unsigned)st.p1_acc ? c2 : (unsigned)st.p1_acc;
+      if (S.Ilafs < st.maxS.Ilafs) return;
+    }
     st.e[0] = st.e[3];
     st.e[3] = d;
     st.maxS = S;
@@ -304,7 +335,7 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
   for (int i = 0; i < 4; ++i) st.e[i] = i;
   st.e[4] = 3;
   for (int i = 0; i < 9; ++i) st.H[i] = 0.0;
-  st.max_sam = P.max_iters; st.iter_cnt = 0; st.iterID = 0; st.no_rej = 0;
+  st.max_sam = P.max_iters; st.iter_cnt = 0; st.iterID = 0; st.no_rej = 0; st.p1_acc = 0;
   st.ht.n = 0;
   st.cur.seed = P.seed; st.cur.k = 0; st.cur.j = 1;
   for (int r = 0; r < 4; ++r)
@@ -366,6 +397,19 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
     for (int j = c.tid; j < (int)Sc.I; j += c.nt) {
       const int i = W.itmp[0][j];
       if (h_resid_symmax_gate(s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]) > P.sym_th) mask_out[i] = 0;
+    }
+    DG_SYNC();
+  }
+  if (P.do_laf) {   // final LAF prune (exp_ranH.c:889-907): both helper correspondences, indexed by correspondence
+    const Score Sc = blk_inlidxs(c, d, P.th, W.itmp[0]);
+    HSym s;
+    if (P.metric != H_SAMPSON) h_sym_prepare(st.H, &s);
+    #pragma unroll 1
+    for (int j = c.tid; j < (int)Sc.I; j += c.nt) {
+      const int i = W.itmp[0][j];
+      const double e1 = h_resid_laf(P.metric, st.H, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i], c.laf[0][i], c.laf[1][i], c.laf[2][i], c.laf[3][i]);
+      const double e2 = h_resid_laf(P.metric, st.H, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i], c.laf[4][i], c.laf[5][i], c.laf[6][i], c.laf[7][i]);
+      if (e1 > P.th_laf || e2 > P.th_laf) mask_out[i] = 0;
     }
     DG_SYNC();
   }

@@ -102,6 +102,50 @@ DG_HD double h_resid_metric(int metric, const double* H, const HSym& s, double x
   const double m = d1 < d2 ? d2 : d1;
   return metric == H_SYMM_SQ_MAX ? m : sqrt(m);
 }
+// Residual of a LAF helper correspondence as the reference's "i"/"idx" metric variants compute it
+// (HDsi/HDsidx and the four HDsi*Sym* / HDs*Sym*idx, Htools.c:372-815).  Two quirks are reproduced:
+//   * Sampson: the linearised residual pair comes from the rows Z of the MAIN correspondence (the drivers pass
+//     `Z` built from `u` together with the helper array `u_1`/`u_2`), only the Jacobian uses the helper point;
+//   * symmetric metrics: helper point only, and ALL four variants add 1e-10 to both denominators (the full-pass
+//     Max / MaxSq metrics do not).
+DG_HD double h_resid_laf(int metric, const double* H, const HSym& s, double x1, double y1, double x2, double y2,
+                         double hx1, double hy1, double hx2, double hy2) {
+  if (metric == H_SAMPSON) {
+    double r1 = 0.0, r2 = 0.0;
+    r1 += H[0] * x2;
+    r2 += H[1] * x2;
+    r1 += H[2] * (-x1 * x2);
+    r2 += H[2] * (-y1 * x2);
+    r1 += H[3] * y2;
+    r2 += H[4] * y2;
+    r1 += H[5] * (-x1 * y2);
+    r2 += H[5] * (-y1 * y2);
+    r1 += H[6] * 1.0;
+    r2 += H[7] * 1.0;
+    r1 += H[8] * (-x1 * 1.0);
+    r2 += H[8] * (-y1 * 1.0);
+    const double a = H[0] - H[2] * hx1;
+    const double b = H[3] - H[5] * hx1;
+    const double c = -H[8] - H[2] * hx2 - H[5] * hy2;
+    const double d = H[1] - H[2] * hy1;
+    const double e = H[4] - H[5] * hy1;
+    double pJ[8];
+    h_pinvJ(a, b, c, d, e, pJ);
+    double p = 0.0;
+    for (int j = 0; j < 4; ++j) {
+      const double t = pJ[j] * r1 + pJ[j + 4] * r2;
+      p += t * t;
+    }
+    return p;
+  }
+  double d1, d2;
+  h_sym_d1d2(s, hx1, hy1, hx2, hy2, 1e-10, &d1, &d2);
+  if (metric == H_SYMM_SQ_SUM) return d1 + d2;
+  if (metric == H_SYMM_SUM) return sqrt(d1) + sqrt(d2);
+  const double m = d1 < d2 ? d2 : d1;
+  return metric == H_SYMM_SQ_MAX ? m : sqrt(m);
+}
+
 // Symmetric-consistency gate metric: always HDsSymMaxidx, WITH the 1e-10 (Htools.c:734-774).
 DG_HD double h_resid_symmax_gate(const HSym& s, double x1, double y1, double x2, double y2) {
   double d1, d2;

@@ -84,3 +84,13 @@ def scene_F_laf(n=600, inlier_ratio=0.5, seed=0, jitter=0.6, plane_frac=0.0):
     A2 = A1 + rng.normal(0, jitter, (n, 4))
     A2[~gt] = rng.normal(0, 6, ((~gt).sum(), 4))
     return np.hstack([p1, A1]), np.hstack([p2, A2]), gt
+
+
+def scene_H_laf(n=800, n_in=400, seed=0, jitter=0.6):
+    """scene_H plus local affine frames ([N,6] rows), as scene_F_laf."""
+    p1, p2, gt = scene_H(n, n_in, seed)
+    rng = np.random.default_rng(seed + 1000)
+    A1 = np.tile(np.array([6.0, 0.0, 0.0, 6.0]), (n, 1)) + rng.normal(0, 1.0, (n, 4))
+    A2 = A1 + rng.normal(0, jitter, (n, 4))
+    A2[~gt] = rng.normal(0, 6, ((~gt).sum(), 4))
+    return np.hstack([p1, A1]), np.hstack([p2, A2]), gt

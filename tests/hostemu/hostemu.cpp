@@ -80,12 +80,13 @@ extern "C" int emu_find_homography(const double* x1y1, const double* x2y2, int n
                                    int max_iters, int error_type, int sym_check, double laf_coef, uint64_t seed,
                                    int chunk, double* H, unsigned char* mask, int* stats) {
   if (n < 4 || (dim != 2 && dim != 6)) return -1;
-  if (laf_coef > 0) return -3;
+  if (laf_coef > 0 && dim != 6) return -1;
   Emu E;
   emu_setup(E, x1y1, x2y2, n, dim, chunk);
   HParams P;
   if (h_thresholds(error_type, px_th, sym_check, &P.th, &P.sym_th)) return -2;
-  P.conf = conf; P.laf_coef = 0; P.max_iters = max_iters; P.metric = error_type;
+  P.conf = conf; P.laf_coef = laf_coef; P.max_iters = max_iters; P.metric = error_type;
+  P.do_laf = laf_coef > 0 ? 1 : 0; P.th_laf = laf_coef * P.th;
   P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk;
   ransac_H_pair(E.c, P, E.W, H, mask, stats);
   free(E.slab); free(E.tile);

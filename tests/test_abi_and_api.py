@@ -39,8 +39,8 @@ def test_argument_errors_before_any_cuda_call():
     p = np.zeros((1, 10, 2))
     with pytest.raises(ValueError):   # unknown metric
         _cabi.homography_batch(p, p, 1.0, 0.99, 10, 7, True, 0.0, None)
-    with pytest.raises(ValueError):   # LAF gate on homographies: explicit "unsupported", never a silent skip
-        _cabi.homography_batch(np.zeros((1, 10, 6)), np.zeros((1, 10, 6)), 1.0, 0.99, 10, 0, True, 3.0, None)
+    with pytest.raises(ValueError):   # LAF gate needs the [n,6] layout (homography too)
+        _cabi.homography_batch(np.zeros((1, 10, 2)), np.zeros((1, 10, 2)), 1.0, 0.99, 10, 0, True, 3.0, None)
     with pytest.raises(ValueError):   # LAF gate needs the [n,6] layout
         _cabi.fundamental_batch(np.zeros((1, 10, 2)), np.zeros((1, 10, 2)), 1.0, 0.99, 10, 0, True, 3.0, True, None)
 

@@ -178,3 +178,18 @@ def test_F_laf_gate_vs_reference_on_gpu(ref_oracle):
     # [N,2] inputs with laf_coef > 0 are rejected at the C ABI (the Python layer warns and drops the coefficient)
     with pytest.raises(Exception):
         _cabi.fundamental_batch(x1[:, :2].copy(), x2[:, :2].copy(), 1.0, 0.999, 100, 0, True, 1.0, True, [1])
+
+
+def test_H_laf_gate_vs_reference_on_gpu(ref_oracle):
+    """LAF gate of the homography path through the C ABI, all five metrics."""
+    from pydegensac_b200 import _cabi
+    from pydegensac_b200.scenes import scene_H_laf
+    rng = np.random.default_rng(9)
+    for case in range(40):
+        n = int(rng.choice([100, 300, 800])); nin = int(n * float(rng.choice([0.4, 0.6, 0.8]))); seed = int(rng.integers(1 << 20))
+        jitter = float(rng.choice([0.2, 0.6, 1.5])); laf = float(rng.choice([0.5, 1.0, 2.0, 5.0, 20.0])); et = int(rng.integers(5))
+        sym = bool(rng.integers(2)); mi = int(rng.choice([200, 1000, 3000])); px = float(rng.choice([1.0, 3.0]))
+        x1, x2, _ = scene_H_laf(n, nin, seed, jitter)
+        a = ref_oracle.find_homography_raw(x1, x2, px, 0.999, mi, error_type=et, sym_check=sym, laf_coef=laf, seed=seed)
+        H, m, s = _cabi.homography_batch(x1, x2, px, 0.999, mi, et, sym, laf, [seed])
+        _cmp(a, (H[0], m[0], s[0]), "H LAF case %d" % case)

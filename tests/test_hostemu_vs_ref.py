@@ -165,3 +165,25 @@ def test_F_laf_gate_vs_reference(ref_oracle):
         checked += 1
     assert checked >= 25
     assert changed >= 1, "the LAF gate never changed a result: the test scenes do not exercise it"
+
+
+def test_H_laf_gate_vs_reference(ref_oracle):
+    """LAF gate of the homography driver, all five metrics: the reference's quirks (Sampson variant mixing the main
+    correspondence's linearised rows with the helper point's Jacobian, `p1_inliers` accumulating over the whole run,
+    the final prune) must be reproduced for identical masks."""
+    from tests.hostemu import emu
+    from pydegensac_b200.scenes import scene_H_laf
+    rng = np.random.default_rng(9)
+    checked = changed = 0
+    for case in range(40):
+        n = int(rng.choice([100, 300, 800])); nin = int(n * float(rng.choice([0.4, 0.6, 0.8]))); seed = int(rng.integers(1 << 20))
+        jitter = float(rng.choice([0.2, 0.6, 1.5])); laf = float(rng.choice([0.5, 1.0, 2.0, 5.0, 20.0])); et = int(rng.integers(5))
+        sym = bool(rng.integers(2)); mi = int(rng.choice([200, 1000, 3000])); px = float(rng.choice([1.0, 3.0]))
+        x1, x2, _ = scene_H_laf(n, nin, seed, jitter)
+        a = ref_oracle.find_homography_raw(x1, x2, px, 0.999, mi, error_type=et, sym_check=sym, laf_coef=laf, seed=seed)
+        b = emu.find_homography_raw(x1, x2, px, 0.999, mi, et, sym, laf, seed)
+        _cmp(a, b, "H LAF case %d (n=%d laf=%g metric=%d)" % (case, n, laf, et))
+        a0 = ref_oracle.find_homography_raw(x1, x2, px, 0.999, mi, error_type=et, sym_check=sym, laf_coef=0.0, seed=seed)
+        changed += int(not np.array_equal(a[1], a0[1]))
+        checked += 1
+    assert changed >= 5, "the LAF gate hardly changed a result: the test scenes do not exercise it"
