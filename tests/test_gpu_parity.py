@@ -132,6 +132,20 @@ def test_python_api_on_gpu():
     z = np.ones((20, 2))
     Fz, mz = pdg.findFundamentalMatrix(z, z, 1.0, 0.99, 100, seed=1)
     assert np.abs(Fz).sum() == 0 and not any(mz)
+    # [N,6] keypoints with shapes + laf_consistensy_coef through the public API (reference signature, utils.py:111)
+    import warnings
+    from pydegensac_b200 import _cabi
+    from pydegensac_b200.scenes import scene_F_laf
+    x1, x2, _ = scene_F_laf(400, 0.6, 2)
+    Fl, ml = pdg.findFundamentalMatrix(x1, x2, 1.0, 0.999, 2000, laf_consistensy_coef=2.0, seed=3)
+    Fc, mc, _ = _cabi.fundamental_batch(x1, x2, 1.0, 0.999, 2000, 0, True, 2.0, True, [3])
+    assert np.array_equal(Fl, Fc[0]) and np.array_equal(np.asarray(ml), mc[0])
+    with warnings.catch_warnings(record=True) as wlist:    # (x,y) only: the coefficient is dropped with a warning
+        warnings.simplefilter("always")
+        F0, m0 = pdg.findFundamentalMatrix(x1[:, :2], x2[:, :2], 1.0, 0.999, 2000, laf_consistensy_coef=2.0, seed=3)
+        assert any("laf" in str(w.message).lower() for w in wlist)
+    F1, m1 = pdg.findFundamentalMatrix(x1[:, :2], x2[:, :2], 1.0, 0.999, 2000, seed=3)
+    assert np.array_equal(F0, F1) and np.array_equal(np.asarray(m0), np.asarray(m1))
 
 
 def test_host_feed_fallback_gives_identical_results():
