@@ -100,3 +100,62 @@ def test_dogman_cuda():
         F, fmask = pdg.findFundamentalMatrix(D["src"], D["dst"], 0.5, 0.999, 50000, seed=seed)
         assert np.array_equal(np.asarray(fmask), D["F_mask_%d" % seed])
         assert np.linalg.norm(norm_model(F) - norm_model(D["F_%d" % seed])) < TOL
+
+
+# ------------------------------------------------------------------ LAF-consistency gate ([N,6] inputs, laf_coef > 0)
+GL = np.load(os.path.join(HERE, "golden", "golden_laf_v1.npz"))
+META_L = json.loads(str(GL["meta"]))
+
+
+def _inputs_laf(m):
+    from pydegensac_b200.scenes import scene_F_laf, scene_H_laf
+    return (scene_F_laf if m["kind"] == "F" else scene_H_laf)(**m["scene"])[:2]
+
+
+def _check_laf(i, model, mask, stats):
+    gm, gmask, gst = GL["model_%d" % i], GL["mask_%d" % i], GL["stats_%d" % i]
+    assert np.array_equal(np.asarray(mask, bool), gmask.astype(bool)), "inlier mask differs from the reference (LAF case %d)" % i
+    assert np.linalg.norm(norm_model(model) - norm_model(gm)) < TOL
+    assert int(stats[0]) == int(gst[0]) and int(stats[1]) == int(gst[1]), "samples drawn / LO runs differ"
+
+
+@pytest.mark.parametrize("i", range(len(META_L)))
+def test_reference_reproduces_golden_laf(i, ref_oracle):
+    m = META_L[i]
+    p1, p2 = _inputs_laf(m)
+    if m["kind"] == "F":
+        out = ref_oracle.find_fundamental(p1, p2, **m["call"])
+    else:
+        out = ref_oracle.find_homography_raw(p1, p2, **m["call"])
+    _check_laf(i, *out)
+
+
+@pytest.mark.parametrize("i", range(len(META_L)))
+def test_host_emulation_matches_golden_laf(i):
+    from tests.hostemu import emu
+    m = META_L[i]
+    p1, p2 = _inputs_laf(m)
+    k = m["call"]
+    if m["kind"] == "F":
+        out = emu.find_fundamental(p1, p2, k["px_th"], k["conf"], k["max_iters"], k["error_type"], k["sym_check"], k["laf_coef"],
+                                   k["degen_check"], k["seed"])
+    else:
+        out = emu.find_homography_raw(p1, p2, k["px_th"], k["conf"], k["max_iters"], k["error_type"], k["sym_check"], k["laf_coef"],
+                                      k["seed"])
+    _check_laf(i, *out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(len(META_L)))
+def test_cuda_engine_matches_golden_laf(i):
+    from pydegensac_b200 import _cabi
+    m = META_L[i]
+    p1, p2 = _inputs_laf(m)
+    k = m["call"]
+    if m["kind"] == "F":
+        M, mask, st = _cabi.fundamental_batch(p1, p2, k["px_th"], k["conf"], k["max_iters"], k["error_type"], k["sym_check"],
+                                              k["laf_coef"], k["degen_check"], [k["seed"]])
+    else:
+        M, mask, st = _cabi.homography_batch(p1, p2, k["px_th"], k["conf"], k["max_iters"], k["error_type"], k["sym_check"],
+                                             k["laf_coef"], [k["seed"]])
+    _check_laf(i, M[0], mask[0], st[0])
