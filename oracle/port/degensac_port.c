@@ -421,6 +421,37 @@ static double hres(int metric, const double *H, const HS *s, const Pts *P, int i
 }
 static void hres_all(int metric, const double *H, const Pts *P, double *d) { HS s; if (metric) hsym(H, &s); for (int i = 0; i < P->n; ++i) d[i] = hres(metric, H, &s, P, i); }
 static double hgate(const HS *s, const Pts *P, int i) { double d1, d2; hd1d2(s, P, i, 1e-10, &d1, &d2); return sqrt(d1 < d2 ? d2 : d1); }   /* HDsSymMaxidx :734 */
+/* Residual of a LAF helper correspondence as the "i"/"idx" metric variants compute it (Htools.c:372-815): for the
+ * Sampson metric the linearised pair comes from the rows Z of the MAIN correspondence and only the Jacobian from the
+ * helper point; the four symmetric variants use the helper point alone and all add 1e-10 to both denominators. */
+static double hres_laf(int metric, const double *H, const HS *s, const Pts *P, const Pts *L, int i) {
+  if (metric == 0) {
+    double r0[9], r1[9], ra = 0, rb = 0, pJ[8];
+    hrows(P, i, r0, r1);
+    for (int j = 0; j < 9; ++j) { ra += H[j] * r0[j]; rb += H[j] * r1[j]; }
+    double x1 = L->x1[i], y1 = L->y1[i], x2 = L->x2[i], y2 = L->y2[i];
+    double a = H[0] - H[2] * x1, b = H[3] - H[5] * x1, c = -H[8] - H[2] * x2 - H[5] * y2, d = H[1] - H[2] * y1, e = H[4] - H[5] * y1;
+    double a2 = a * a, b2 = b * b, c2 = c * c, d2 = d * d, e2 = e * e, c2pd2 = c2 + d2, ab = a * b, de = d * e, Q = c * (c2pd2 + e2);
+    pJ[0] = -b * de + a * (c2 + e2); pJ[1] = b * c2pd2 - a * de; pJ[2] = Q; pJ[3] = -c * (a * d + b * e);
+    pJ[4] = d * (b2 + c2) - ab * e; pJ[5] = -ab * d + e * (a2 + c2); pJ[6] = pJ[3]; pJ[7] = c * (a2 + b2 + c2);
+    double N = a * pJ[0] + b * pJ[1] + c * pJ[2], p = 0;
+    for (int j = 0; j < 8; ++j) pJ[j] /= N;
+    for (int j = 0; j < 4; ++j) { double t = pJ[j] * ra + pJ[j + 4] * rb; p += t * t; }
+    return p;
+  }
+  double d1, d2;
+  hd1d2(s, L, i, 1e-10, &d1, &d2);
+  if (metric == 3) return d1 + d2;
+  if (metric == 4) return sqrt(d1) + sqrt(d2);
+  double m = d1 < d2 ? d2 : d1;
+  return metric == 1 ? m : sqrt(m);
+}
+static int lafcountH(int metric, const double *H, const Pts *P, const Pts *L, const int *list, unsigned n, double th_laf) {
+  HS s; if (metric) hsym(H, &s);
+  int c = 0;
+  for (unsigned j = 0; j < n; ++j) if (hres_laf(metric, H, &s, P, L, list[j]) <= th_laf) ++c;
+  return c;
+}
 static int ori_ok_H(const Pts *P, const int *idx) {   /* all_Hori_valid :821-848 */
   double A[4][3], B[4][3], p[3], q[3];
   for (int i = 0; i < 4; ++i) { A[i][0] = P->x1[idx[i]]; A[i][1] = P->y1[idx[i]]; A[i][2] = 1; B[i][0] = P->x2[idx[i]]; B[i][1] = P->y2[idx[i]]; B[i][2] = 1; }
@@ -672,15 +703,36 @@ static void soa(const double *x1y1, const double *x2y2, int n, int dim, double *
   P->n = n; P->x1 = b; P->y1 = b + n; P->x2 = b + 2 * n; P->y2 = b + 3 * n; *buf = b;
 }
 
+/* LAF helper correspondences (bindings.cpp:337-389): p1 = x + (a12, a22), p2 = x + (a11, a21) in each image */
+static void soa_laf(const double *x1y1, const double *x2y2, int n, double **buf, Pts *L1, Pts *L2) {
+  double *b = malloc(8 * (size_t)n * sizeof(double));
+  for (int i = 0; i < n; ++i) {
+    const double *q1 = x1y1 + 6 * (size_t)i, *q2 = x2y2 + 6 * (size_t)i;
+    b[i] = q1[0] + q1[3]; b[n + i] = q1[1] + q1[5]; b[2 * n + i] = q2[0] + q2[3]; b[3 * n + i] = q2[1] + q2[5];
+    b[4 * n + i] = q1[0] + q1[2]; b[5 * n + i] = q1[1] + q1[4]; b[6 * n + i] = q2[0] + q2[2]; b[7 * n + i] = q2[1] + q2[4];
+  }
+  L1->n = n; L1->x1 = b; L1->y1 = b + n; L1->x2 = b + 2 * n; L1->y2 = b + 3 * n;
+  L2->n = n; L2->x1 = b + 4 * n; L2->y1 = b + 5 * n; L2->x2 = b + 6 * n; L2->y2 = b + 7 * n; *buf = b;
+}
+/* F LAF gate count (exp_ranF.c:1394-1412): min(#p2 passing, #p1 passing) with the run's own metric (FDS1idx) */
+static unsigned lafcountF(int metric, const double *F, const Pts *L1, const Pts *L2, const int *list, unsigned n, double th_laf) {
+  unsigned c1 = 0, c2 = 0;
+  for (unsigned j = 0; j < n; ++j) { if (fres(metric, F, L1, list[j]) <= th_laf) ++c1; if (fres(metric, F, L2, list[j]) <= th_laf) ++c2; }
+  return c2 < c1 ? c2 : c1;
+}
+
 int port_find_fundamental(const double *x1y1, const double *x2y2, int n, int dim, double px_th, double conf, int max_iters,
                           int error_type, int sym_check, double laf_coef, int degen, uint64_t seed, double *F_out,
                           unsigned char *mask, int *stats) {
   if (n < 8 || (dim != 2 && dim != 6)) return -1;
-  if (laf_coef > 0) return -3;
+  if (laf_coef > 0 && dim != 6) return -1;
   double *pb; Pts P; soa(x1y1, x2y2, n, dim, &pb, &P);
+  const int do_laf = laf_coef > 0;                         /* exp_ranF.c:1271-1272 */
+  double *lb = NULL; Pts L1, L2; if (do_laf) soa_laf(x1y1, x2y2, n, &lb, &L1, &L2);
   FP fp = {error_type, px_th * px_th, px_th * px_th * (3.0 * (sym_check ? 1 : 0)), conf, 0, degen};   /* bindings.cpp:299-318 */
   fp.do_sym = fp.sym_th > 0;
   double th = fp.th;
+  const double th_laf = laf_coef * th;
   double *err = calloc(4 * (size_t)n, sizeof(double)), *errs[5] = {err, err + n, err + 2 * n, err + 3 * n, err + 3 * n};
   double *errorsBest = calloc(n, sizeof(double)), *w = malloc(n * sizeof(double)), *HDsb = malloc(n * sizeof(double));
   int *inliers = malloc(n * sizeof(int)); unsigned char *hmask = calloc(n, 1);
@@ -710,6 +762,7 @@ int port_find_fundamental(const double *x1y1, const double *x2y2, int n, int dim
       S = inlidxs(d, n, th, inliers);
       if (maxS.J < S.J) {   /* :1381-1421 */
         if (fp.do_sym) { S.Is = symcountF(f, &P, inliers, S.I, fp.sym_th); if (S.Is < maxS.Is) continue; }
+        if (do_laf) { S.Ilafs = lafcountF(fp.metric, f, &L1, &L2, inliers, S.I, th_laf); if (S.Ilafs < maxS.Ilafs) continue; }   /* :1394-1412 */
         errs[i] = errs[3]; errs[3] = d; maxS = S; memcpy(F, f, 72); new_max = 1;
       }
       if (maxSs.J < S.J) {   /* :1425-1492 */
@@ -753,6 +806,7 @@ int port_find_fundamental(const double *x1y1, const double *x2y2, int n, int dim
       if (maxS.J < S.J) {
         int upd = 1;
         if (fp.do_sym) { S.Is = symcountF(f, &P, inliers, S.I, fp.sym_th); if (S.Is < maxS.Is) upd = 0; }
+        if (do_laf && upd) { S.Ilafs = lafcountF(fp.metric, f, &L1, &L2, inliers, S.I, th_laf); if (S.Ilafs < maxS.Ilafs) upd = 0; }   /* :1536-1555 */
         if (upd) { d = errs[0]; errs[0] = errs[3]; errs[3] = d; maxS = S; memcpy(F, f, 72); new_max = 1; }
       }
       if (new_max) { int ns = nsamples((int)maxS.I + 1, n, 7, conf); if (ns < max_sam) max_sam = ns; }   /* nested in do_iterate: App. A#3 */
@@ -792,6 +846,7 @@ int port_find_fundamental(const double *x1y1, const double *x2y2, int n, int dim
       if (maxS.J < S.J) {
         int upd = 1;
         if (fp.do_sym) { S.Is = symcountF(f, &P, inliers, S.I, fp.sym_th); if (S.Is < maxS.Is) upd = 0; }
+        if (do_laf && upd) { S.Ilafs = lafcountF(fp.metric, f, &L1, &L2, inliers, S.I, th_laf); if (S.Ilafs < maxS.Ilafs) upd = 0; }   /* :1664-1683 */
         if (upd) { d = errs[0]; errs[0] = errs[3]; errs[3] = d; maxS = S; memcpy(F, f, 72); }
       }
     }
@@ -802,12 +857,14 @@ int port_find_fundamental(const double *x1y1, const double *x2y2, int n, int dim
   double asum = 0; for (int i = 0; i < 9; ++i) { F_out[i] = F[i]; asum += fabs(F[i]); }
   if (asum == 0) memset(mask, 0, n);
   if (stats) { stats[0] = no_sam; stats[1] = iter_cnt; stats[2] = Ihmax; stats[3] = (int)maxS.I; }
-  free(pb); free(err); free(errorsBest); free(w); free(HDsb); free(inliers); free(hmask); free(ht.h); free(ht.len); free(ht.id);
+  /* (the final LAF prune, :1724-1740, is guarded by a function-scope `do_update` that is never assigned: undefined
+      behaviour; in the compiled reference it never runs, and it is not restated) */
+  free(pb); free(lb); free(err); free(errorsBest); free(w); free(HDsb); free(inliers); free(hmask); free(ht.h); free(ht.len); free(ht.id);
   return 0;
 }
 
 /* ------------------------------------------------------------------ H: LO (exp_ranH.c:291-467) and driver (:470-930) */
-typedef struct { int metric; double th, sym_th, conf; int do_sym; } HP;
+typedef struct { int metric; double th, sym_th, conf; int do_sym; int do_laf; double th_laf; const Pts *L1, *L2; int *p1_inliers; } HP;
 static Sc iterHc(const Pts *P, const HP *hp, int *inl, double th, double ths, double *H, double **errs, int id, HT *ht) {
   double *d = errs[1], h[9], dth = (ths - th) / ILSQ; int n = P->n;
   Sc S = {0, 0, 0, 0}, Ss, maxS = inlidxs(errs[4], n, th, inl);
@@ -860,6 +917,13 @@ static int lo_step_H(const Pts *P, const HP *hp, double **errs, int *inliers, in
       for (unsigned j = 0; j < Sc2.I; ++j) if (hgate(&s, P, inliersS[j]) <= hp->sym_th) ++S.Is;
       if (S.Is < maxS->Is) upd = 0;
     }
+    if (upd && hp->do_laf) {   /* :718-736 / :834-849; `p1_inliers` is never reset in the reference: it accumulates */
+      Sc Sc2 = inlidxs(d, n, hp->th, inliersS);
+      *hp->p1_inliers += lafcountH(hp->metric, h, P, hp->L1, inliersS, Sc2.I, hp->th_laf);
+      unsigned c2 = (unsigned)lafcountH(hp->metric, h, P, hp->L2, inliersS, Sc2.I, hp->th_laf);
+      S.Ilafs = c2 < (unsigned)*hp->p1_inliers ? c2 : (unsigned)*hp->p1_inliers;
+      if (S.Ilafs < maxS->Ilafs) upd = 0;
+    }
     if (upd) { double *t = errs[0]; errs[0] = errs[3]; errs[3] = t; *maxS = S; memcpy(Hbest, h, 72); new_max = 1; }
   }
   return new_max;
@@ -869,13 +933,16 @@ int port_find_homography(const double *x1y1, const double *x2y2, int n, int dim,
                          int *stats) {
   if (n < 4 || (dim != 2 && dim != 6)) return -1;
   if (error_type < 0 || error_type > 4) return -2;
-  if (laf_coef > 0) return -3;
+  if (laf_coef > 0 && dim != 6) return -1;
   double *pb; Pts P; soa(x1y1, x2y2, n, dim, &pb, &P);
+  double *lb = NULL; Pts L1, L2; int p1_inliers = 0;
+  if (laf_coef > 0) soa_laf(x1y1, x2y2, n, &lb, &L1, &L2);
   double coef = 3.0 * (sym_check ? 1 : 0);   /* bindings.cpp:64-107 */
-  HP hp = {error_type, 0, 0, conf, 0};
+  HP hp = {error_type, 0, 0, conf, 0, laf_coef > 0, 0, &L1, &L2, &p1_inliers};
   switch (error_type) { case 0: hp.th = px_th * px_th; hp.sym_th = px_th * coef; break; case 1: hp.th = px_th * px_th; break; case 2: hp.th = px_th; break;
                         case 3: hp.th = px_th * px_th; hp.sym_th = px_th * coef; break; default: hp.th = px_th; hp.sym_th = px_th * coef; }
   hp.do_sym = hp.sym_th > 0;
+  hp.th_laf = laf_coef * hp.th;   /* exp_ranH.c:500 */
   double th = hp.th, *err = calloc(4 * (size_t)n, sizeof(double)), *errs[5] = {err, err + n, err + 2 * n, err + 3 * n, err + 3 * n};
   int *inliers = malloc(n * sizeof(int)), *inliersS = malloc(n * sizeof(int));
   HT ht = {malloc(64 * 4), malloc(64 * 4), malloc(64 * 4), 0, 64};
@@ -901,6 +968,13 @@ int port_find_homography(const double *x1y1, const double *x2y2, int n, int dim,
     S = inlidxs(d, n, th, inliersS);
     if (maxS.J < S.J) {   /* :585-627 */
       if (hp.do_sym) { HS s; hsym(h, &s); S.Is = 0; for (unsigned j = 0; j < S.I; ++j) if (hgate(&s, &P, inliersS[j]) <= hp.sym_th) ++S.Is; if (S.Is < maxS.Is) continue; }
+      if (hp.do_laf) {   /* :600-619 */
+        p1_inliers += lafcountH(hp.metric, h, &P, &L1, inliersS, S.I, hp.th_laf);
+        if ((unsigned)p1_inliers < maxS.Ilafs) continue;
+        unsigned c2 = (unsigned)lafcountH(hp.metric, h, &P, &L2, inliersS, S.I, hp.th_laf);
+        S.Ilafs = c2 < (unsigned)p1_inliers ? c2 : (unsigned)p1_inliers;
+        if (S.Ilafs < maxS.Ilafs) continue;
+      }
       errs[0] = errs[3]; errs[3] = d; maxS = S; new_max = 1; memcpy(H, h, 72);
     }
     if (maxSs.J < S.J) { do_iterate = no_sam > ITER_SAM; maxSs = S; errs[4] = d; } else do_iterate = 0;
@@ -912,10 +986,14 @@ int port_find_homography(const double *x1y1, const double *x2y2, int n, int dim,
   if (iter_cnt == 0) { ++iter_cnt; memcpy(h, H, 72); lo_step_H(&P, &hp, errs, inliers, inliersS, h, H, &maxS, &iterID, &ht, &st); }   /* :759-862 */
   { double *d = errs[3];
     for (int j = 0; j < n; ++j) mask[j] = d[j] <= th;
-    if (hp.do_sym) { Sc Sc2 = inlidxs(d, n, th, inliersS); HS s; hsym(H, &s); for (unsigned j = 0; j < Sc2.I; ++j) if (hgate(&s, &P, inliersS[j]) > hp.sym_th) mask[inliersS[j]] = 0; } }
+    if (hp.do_sym) { Sc Sc2 = inlidxs(d, n, th, inliersS); HS s; hsym(H, &s); for (unsigned j = 0; j < Sc2.I; ++j) if (hgate(&s, &P, inliersS[j]) > hp.sym_th) mask[inliersS[j]] = 0; }
+    if (hp.do_laf) {   /* final LAF prune, :889-907 (HDSidx1 on both helper correspondences) */
+      Sc Sc2 = inlidxs(d, n, th, inliersS); HS s; if (hp.metric) hsym(H, &s);
+      for (unsigned j = 0; j < Sc2.I; ++j) { int i = inliersS[j];
+        if (hres_laf(hp.metric, H, &s, &P, &L1, i) > hp.th_laf || hres_laf(hp.metric, H, &s, &P, &L2, i) > hp.th_laf) mask[i] = 0; } } }
   double asum = 0; for (int i = 0; i < 9; ++i) { H_out[i] = H[i]; asum += fabs(H[i]); }
   if (asum == 0) memset(mask, 0, n);
   if (stats) { stats[0] = no_sam; stats[1] = iter_cnt; stats[2] = no_rej; stats[3] = (int)maxS.I; }
-  free(pb); free(err); free(inliers); free(inliersS); free(ht.h); free(ht.len); free(ht.id);
+  free(pb); free(lb); free(err); free(inliers); free(inliersS); free(ht.h); free(ht.len); free(ht.id);
   return 0;
 }

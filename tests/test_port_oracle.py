@@ -59,3 +59,19 @@ def test_port_vs_reference_randomised(ref_oracle):
             continue
         assert np.array_equal(a[1], b[1]), "case %d %s" % (case, kind)
         assert np.linalg.norm(norm_model(a[0]) - norm_model(b[0])) < 1e-6
+
+
+def test_port_laf_gate_matches_golden_laf():
+    """The plain-C restatement reproduces the LAF-gate golden vectors (produced by the unmodified reference)."""
+    import json
+    import os
+    from oracle import port
+    from pydegensac_b200.scenes import scene_F_laf, scene_H_laf
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_laf_v1.npz"))
+    meta = json.loads(str(G["meta"]))
+    for i, m in enumerate(meta):
+        p1, p2 = (scene_F_laf if m["kind"] == "F" else scene_H_laf)(**m["scene"])[:2]
+        out = (port.find_fundamental if m["kind"] == "F" else port.find_homography_raw)(p1, p2, **m["call"])
+        assert np.array_equal(out[1], G["mask_%d" % i].astype(bool)), "mask differs (LAF case %d)" % i
+        assert np.linalg.norm(norm_model(out[0]) - norm_model(G["model_%d" % i])) < 1e-6
+        assert int(out[2][0]) == int(G["stats_%d" % i][0]) and int(out[2][1]) == int(G["stats_%d" % i][1])
