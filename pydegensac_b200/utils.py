@@ -161,27 +161,37 @@ def _batch_seeds(seeds, P):
     return seeds
 
 
+def _batch_laf(coef, p1):
+    """The single-pair API's treatment of laf_consistensy_coef (utils.py:87-89, 116): dropped with a warning for
+    (x, y)-only keypoints, clamped at 0."""
+    if p1.shape[-1] == 2 and coef > 0:
+        warnings.warn('You set laf_consistensy_coef, but provided only (x,y) keypoints. Skipping LAF check')
+        coef = 0
+    return max(0, coef)
+
+
 def findFundamentalMatrixBatch(pts1, pts2, px_th=0.5, conf=0.9999, max_iters=100000, error_type="sampson",
                                symmetric_error_check=True, enable_degeneracy_check=True, seeds=None,
-                               return_stats=False):
-    """Batched findFundamentalMatrix over P independent pairs: pts [P,N,2] -> (F [P,3,3], mask [P,N] bool).
-    Pairs without a model get an all-zero F and an all-False mask row."""
+                               return_stats=False, laf_consistensy_coef=-1.0):
+    """Batched findFundamentalMatrix over P independent pairs: pts [P,N,2] (or [P,N,6] with local affine shapes)
+    -> (F [P,3,3], mask [P,N] bool).  Pairs without a model get an all-zero F and an all-False mask row."""
     from . import _cabi
     et = _error_type(error_type, error_type_dict_fundamental)
     p1 = np.asarray(pts1)
-    F, mask, stats = _cabi.fundamental_batch(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check, 0.0,
+    F, mask, stats = _cabi.fundamental_batch(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check,
+                                             _batch_laf(laf_consistensy_coef, p1),
                                              enable_degeneracy_check, _batch_seeds(seeds, p1.shape[0]))
     return (F, mask, stats) if return_stats else (F, mask)
 
 
 def findHomographyBatch(pts1, pts2, px_th=1.0, conf=0.999, max_iters=50000, error_type="sampson",
-                        symmetric_error_check=True, seeds=None, return_stats=False):
-    """Batched findHomography: pts [P,N,2] -> (H [P,3,3] OpenCV convention, mask [P,N] bool)."""
+                        symmetric_error_check=True, seeds=None, return_stats=False, laf_consistensy_coef=-1.0):
+    """Batched findHomography: pts [P,N,2] (or [P,N,6]) -> (H [P,3,3] OpenCV convention, mask [P,N] bool)."""
     from . import _cabi
     et = _error_type(error_type, error_type_dict_homography)
     p1 = np.asarray(pts1)
-    Hraw, mask, stats = _cabi.homography_batch(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check, 0.0,
-                                               _batch_seeds(seeds, p1.shape[0]))
+    Hraw, mask, stats = _cabi.homography_batch(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check,
+                                               _batch_laf(laf_consistensy_coef, p1), _batch_seeds(seeds, p1.shape[0]))
     H = np.zeros_like(Hraw)
     for i in range(Hraw.shape[0]):
         if np.abs(Hraw[i]).sum() != 0:

@@ -146,6 +146,10 @@ def test_python_api_on_gpu():
         assert any("laf" in str(w.message).lower() for w in wlist)
     F1, m1 = pdg.findFundamentalMatrix(x1[:, :2], x2[:, :2], 1.0, 0.999, 2000, seed=3)
     assert np.array_equal(F0, F1) and np.array_equal(np.asarray(m0), np.asarray(m1))
+    # batched entry points take the coefficient too
+    Fb2, mb2 = pdg.findFundamentalMatrixBatch(np.stack([x1, x1]), np.stack([x2, x2]), 1.0, 0.999, 2000, seeds=[3, 3],
+                                              laf_consistensy_coef=2.0)
+    assert np.array_equal(Fb2[0], Fl) and np.array_equal(mb2[1], np.asarray(ml))
 
 
 def test_host_feed_fallback_gives_identical_results():
