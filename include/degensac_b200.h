@@ -65,7 +65,10 @@ int dgb200_find_homography_batch(const double* x1y1, const double* x2y2, int n_p
                                  double* H_out, uint8_t* mask_out, int32_t* stats_out);
 
 /* Same two paths with DEVICE pointers (inputs already resident in HBM, outputs left in HBM) on a CUDA
- * stream (cudaStream_t passed as void*; NULL = default stream).  Asynchronous: returns after enqueueing. */
+ * stream (cudaStream_t passed as void*; NULL = default stream).  Asynchronous: returns after enqueueing.
+ * Re-entrant: every launch in flight owns its scratch slabs and work counter (a pool keyed by stream), so calls on
+ * different streams -- F and H mixed -- may overlap; calls on one stream are ordered by the stream.  Input pointers
+ * need only the natural 8-byte alignment of float64 (16-byte aligned [n,2] inputs are read with 128-bit loads). */
 int dgb200_find_fundamental_batch_dev(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
                                       double px_th, double conf, int max_iters, int error_type, int sym_check,
                                       double laf_coef, int degen_check, const uint64_t* d_seeds,
@@ -74,6 +77,30 @@ int dgb200_find_homography_batch_dev(const double* d_x1y1, const double* d_x2y2,
                                      double px_th, double conf, int max_iters, int error_type, int sym_check,
                                      double laf_coef, const uint64_t* d_seeds,
                                      double* d_H_out, uint8_t* d_mask_out, int32_t* d_stats_out, void* stream);
+
+/* Ragged batches (proposal 3): real tentative sets never share n.  The correspondences of all
+ * pairs are concatenated ([offsets[n_pairs]][dim] float64); pair p owns rows offsets[p] .. offsets[p+1]-1
+ * (offsets[0] = 0, int32, every pair n >= 8 for F / n >= 4 for H); mask_out is concatenated the same way
+ * ([offsets[n_pairs]] uint8); models and stats stay [n_pairs][9] / [n_pairs][4].  Same kernel, same results as one
+ * call per pair.  HOST buffers; synchronous. */
+int dgb200_find_fundamental_ragged(const double* x1y1, const double* x2y2, const int32_t* offsets, int n_pairs, int dim,
+                                   double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                   double laf_coef, int degen_check, const uint64_t* seeds,
+                                   double* F_out, uint8_t* mask_out, int32_t* stats_out);
+int dgb200_find_homography_ragged(const double* x1y1, const double* x2y2, const int32_t* offsets, int n_pairs, int dim,
+                                  double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                  double laf_coef, const uint64_t* seeds,
+                                  double* H_out, uint8_t* mask_out, int32_t* stats_out);
+/* DEVICE-pointer flavour of the ragged batches (d_offsets in device memory; n_max = the largest pair, it sizes the
+ * per-CTA scratch).  Asynchronous on `stream`. */
+int dgb200_find_fundamental_ragged_dev(const double* d_x1y1, const double* d_x2y2, const int32_t* d_offsets, int n_pairs,
+                                       int n_max, int dim, double px_th, double conf, int max_iters, int error_type,
+                                       int sym_check, double laf_coef, int degen_check, const uint64_t* d_seeds,
+                                       double* d_F_out, uint8_t* d_mask_out, int32_t* d_stats_out, void* stream);
+int dgb200_find_homography_ragged_dev(const double* d_x1y1, const double* d_x2y2, const int32_t* d_offsets, int n_pairs,
+                                      int n_max, int dim, double px_th, double conf, int max_iters, int error_type,
+                                      int sym_check, double laf_coef, const uint64_t* d_seeds,
+                                      double* d_H_out, uint8_t* d_mask_out, int32_t* d_stats_out, void* stream);
 
 /* One pair (what one findFundamentalMatrix_/findHomography_ call does): batch of 1 with one seed. */
 int dgb200_find_fundamental(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
@@ -87,7 +114,7 @@ int dgb200_find_homography(const double* x1y1, const double* x2y2, int n, int di
 int dgb200_version(void);              /* ABI version */
 int dgb200_device_count(void);         /* CUDA devices visible (0 or <0: the engine cannot run) */
 int dgb200_set_device(int device);     /* device used by subsequent calls of this thread's process */
-const char* dgb200_last_error(void);   /* last error message (static storage) */
+const char* dgb200_last_error(void);   /* last error message of the calling thread (thread-local storage) */
 long long dgb200_kernel_launches(void);/* RANSAC kernels launched so far by this process */
 double dgb200_last_kernel_ms(void);    /* device time of the most recent HOST-buffer call's kernel (CUDA events) */
 void dgb200_release(void);             /* free cached device buffers */

@@ -35,6 +35,10 @@ def lib():
         vp = ctypes.c_void_p
         L.dgb200_find_fundamental_batch_dev.argtypes = [vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, ci, vp, vp, vp, vp, vp]
         L.dgb200_find_homography_batch_dev.argtypes = [vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, vp, vp, vp, vp, vp]
+        L.dgb200_find_fundamental_ragged.argtypes = [dp, dp, i32, ci, ci, cd, cd, ci, ci, ci, cd, ci, u64, dp, u8, i32]
+        L.dgb200_find_homography_ragged.argtypes = [dp, dp, i32, ci, ci, cd, cd, ci, ci, ci, cd, u64, dp, u8, i32]
+        L.dgb200_find_fundamental_ragged_dev.argtypes = [vp, vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, ci, vp, vp, vp, vp, vp]
+        L.dgb200_find_homography_ragged_dev.argtypes = [vp, vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, vp, vp, vp, vp, vp]
         L.dgb200_last_error.restype = ctypes.c_char_p
         L.dgb200_kernel_launches.restype = ctypes.c_longlong
         L.dgb200_last_kernel_ms.restype = ctypes.c_double
@@ -102,6 +106,58 @@ def homography_batch(pts1, pts2, px_th, conf, max_iters, error_type, sym_check, 
     if rc != 0:
         _raise(rc)
     return H, mask.view(np.bool_), stats
+
+
+def _ragged_prep(list1, list2):
+    if len(list1) != len(list2) or len(list1) == 0:
+        raise ValueError("expected two equally long, non-empty lists of [n_i, dim] arrays")
+    a1 = [np.ascontiguousarray(a, dtype=np.float64) for a in list1]
+    a2 = [np.ascontiguousarray(a, dtype=np.float64) for a in list2]
+    dim = a1[0].shape[1] if a1[0].ndim == 2 else -1
+    for x, y in zip(a1, a2):
+        if x.ndim != 2 or x.shape != y.shape or x.shape[1] != dim:
+            raise ValueError("every pair needs two arrays of equal shape [n_i, dim] with the same dim across the batch")
+    offsets = np.zeros(len(a1) + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum([x.shape[0] for x in a1])
+    return np.concatenate(a1, 0), np.concatenate(a2, 0), offsets, dim
+
+
+def fundamental_ragged(list1, list2, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check, seeds):
+    """Ragged batch: lists of [n_i, dim] arrays.  Returns (F [P,3,3], list of bool masks, stats [P,4])."""
+    p1, p2, offsets, dim = _ragged_prep(list1, list2)
+    P = len(offsets) - 1
+    F = np.zeros((P, 3, 3), dtype=np.float64)
+    mask = np.zeros(int(offsets[-1]), dtype=np.uint8)
+    stats = np.zeros((P, 4), dtype=np.int32)
+    s = _seeds(seeds, P)
+    rc = lib().dgb200_find_fundamental_ragged(_p(p1, ctypes.c_double), _p(p2, ctypes.c_double), _p(offsets, ctypes.c_int32),
+                                              P, dim, float(px_th), float(conf), int(max_iters), int(error_type),
+                                              int(bool(sym_check)), float(laf_coef), int(bool(degen_check)),
+                                              _p(s, ctypes.c_uint64) if s is not None else None,
+                                              _p(F, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32))
+    if rc != 0:
+        _raise(rc)
+    mb = mask.view(np.bool_)
+    return F, [mb[offsets[i]:offsets[i + 1]] for i in range(P)], stats
+
+
+def homography_ragged(list1, list2, px_th, conf, max_iters, error_type, sym_check, laf_coef, seeds):
+    """Ragged batch: lists of [n_i, dim] arrays.  Returns (RAW H [P,3,3], list of bool masks, stats [P,4])."""
+    p1, p2, offsets, dim = _ragged_prep(list1, list2)
+    P = len(offsets) - 1
+    H = np.zeros((P, 3, 3), dtype=np.float64)
+    mask = np.zeros(int(offsets[-1]), dtype=np.uint8)
+    stats = np.zeros((P, 4), dtype=np.int32)
+    s = _seeds(seeds, P)
+    rc = lib().dgb200_find_homography_ragged(_p(p1, ctypes.c_double), _p(p2, ctypes.c_double), _p(offsets, ctypes.c_int32),
+                                             P, dim, float(px_th), float(conf), int(max_iters), int(error_type),
+                                             int(bool(sym_check)), float(laf_coef),
+                                             _p(s, ctypes.c_uint64) if s is not None else None,
+                                             _p(H, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32))
+    if rc != 0:
+        _raise(rc)
+    mb = mask.view(np.bool_)
+    return H, [mb[offsets[i]:offsets[i + 1]] for i in range(P)], stats
 
 
 def fundamental_batch_dev(d_p1, d_p2, P, N, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check,

@@ -166,6 +166,95 @@ inline void st_row(double* p, double v) { *p = v; }
 inline void prefetch_l1(const void*) {}
 #endif
 
+
+#if DG_DEVICE_PASS
+// Ordered compaction for rows whose per-thread segment would exceed the 8 register-resident residuals of the fast
+// path (long rows: N > 8 x CTA size, e.g. the 5000-correspondence homography batches).  Warp w owns the contiguous
+// chunk [w*chunk, (w+1)*chunk) of the row (chunk a multiple of 32); its lanes stride the chunk 32 residuals at a time,
+// so the loads are coalesced and the ballot of "e <= th" IS the order.  The ballot word of trip j is parked on lane j
+// (chunks up to 1024 residuals), the warp totals are scanned across the CTA, then the parked words are replayed to
+// write the indices -- the row is read once (the thread-segment fallback below reads it twice, uncoalesced).
+// NTH = 1: (S[0], lists[0]) for th[0];  NTH = 2: both thresholds from the same pass.
+template <int NTH>
+__device__ __noinline__ void blk_inlidxs_ballot(const Ctx& c, const double* __restrict__ err, const double* th,
+                                                int* const* lists, Score* S) {
+  const unsigned full = 0xffffffffu;
+  const unsigned lt = (1u << c.lane) - 1u;
+  double wq[NTH], winv[NTH], J[NTH];
+  int off[NTH], cnt[NTH];
+  unsigned parked[NTH];
+#pragma unroll
+  for (int t = 0; t < NTH; ++t) {
+    wq[t] = th[t] * 9 / 4;
+    winv[t] = (th[t] == 0) ? 0.0 : 1.0 / wq[t];
+    J[t] = 0.0; off[t] = 0; cnt[t] = 0; parked[t] = 0u;
+  }
+  const int chunk = (((c.N + c.nw - 1) / c.nw) + 31) & ~31;
+  const int wbeg = c.wid * chunk;
+  const int wend = (wbeg + chunk < c.N) ? wbeg + chunk : c.N;
+  const bool park = chunk <= 1024;
+  #pragma unroll 1
+  for (int base = wbeg, trip = 0; base < wend; base += 32, ++trip) {
+    const int i = base + c.lane;
+    const double e = (i < wend) ? ld_row(err + i) : INFINITY;
+#pragma unroll
+    for (int t = 0; t < NTH; ++t) {
+      if (th[t] != 0 && !(e >= wq[t])) J[t] += 1 - e * winv[t];
+      const unsigned m = __ballot_sync(full, e <= th[t]);
+      if (c.lane == trip) parked[t] = m;
+      cnt[t] += __popc(m);
+    }
+  }
+  DG_SYNC();
+#pragma unroll
+  for (int t = 0; t < NTH; ++t) {
+    const double js = warp_sum(J[t]);
+    if (c.lane == 0) {
+      c.sc->red_i[t * (kMaxWarps / 2) + c.wid] = cnt[t];
+      if (t == 0) c.sc->red_d[c.wid] = js; else c.sc->bc[c.wid] = js;
+    }
+  }
+  DG_SYNC();
+#pragma unroll
+  for (int t = 0; t < NTH; ++t) {
+    int base_off = 0, tot = 0;
+    double jt = 0.0;
+    for (int w = 0; w < c.nw; ++w) {
+      const int v = c.sc->red_i[t * (kMaxWarps / 2) + w];
+      if (w < c.wid) base_off += v;
+      tot += v;
+      jt += (t == 0) ? c.sc->red_d[w] : c.sc->bc[w];
+    }
+    S[t] = make_score(); S[t].J = jt; S[t].I = (unsigned)tot;
+    off[t] = base_off;
+  }
+  if (park) {
+    #pragma unroll 1
+    for (int base = wbeg, trip = 0; base < wend; base += 32, ++trip) {
+#pragma unroll
+      for (int t = 0; t < NTH; ++t) {
+        const unsigned m = __shfl_sync(full, parked[t], trip);
+        if ((m >> c.lane) & 1u) lists[t][off[t] + __popc(m & lt)] = base + c.lane;
+        off[t] += __popc(m);
+      }
+    }
+  } else {
+    #pragma unroll 1
+    for (int base = wbeg; base < wend; base += 32) {
+      const int i = base + c.lane;
+      const double e = (i < wend) ? ld_row(err + i) : INFINITY;
+#pragma unroll
+      for (int t = 0; t < NTH; ++t) {
+        const unsigned m = __ballot_sync(full, e <= th[t]);
+        if ((m >> c.lane) & 1u) lists[t][off[t] + __popc(m & lt)] = i;
+        off[t] += __popc(m);
+      }
+    }
+  }
+  DG_SYNC();
+}
+#endif
+
 DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list) {
   DG_PROF_BEGIN(21);
   DG_PROF_COUNT(22, 1);
@@ -197,6 +286,16 @@ DG_ENGN Score blk_inlidxs(const Ctx& c, const double* err, double th, int* list)
     for (int j = 0; j < 8; ++j)
       if (e[j] <= th) list[off++] = beg + j;
   } else {
+#if DG_DEVICE_PASS
+    if (c.nw <= kMaxWarps / 2) {
+      const double tha[1] = {th};
+      int* const la[1] = {list};
+      Score Sa[1];
+      blk_inlidxs_ballot<1>(c, err, tha, la, Sa);
+      DG_PROF_END(21);
+      return Sa[0];
+    }
+#endif
     #pragma unroll 1
     for (int i = beg; i < end; ++i) {
       const double e = ld_row(err + i);
@@ -223,6 +322,16 @@ DG_ENGN void blk_inlidxs2(const Ctx& c, const double* err, double thA, int* list
                           Score* SB) {
   const int per = (c.N + c.nt - 1) / c.nt;
   if (per > 8 || c.N >= 65536) {
+#if DG_DEVICE_PASS
+    if (c.nw <= kMaxWarps / 2) {
+      const double tha[2] = {thA, thB};
+      int* const la[2] = {listA, listB};
+      Score Sa[2];
+      blk_inlidxs_ballot<2>(c, err, tha, la, Sa);
+      *SA = Sa[0]; *SB = Sa[1];
+      return;
+    }
+#endif
     *SA = blk_inlidxs(c, err, thA, listA);
     *SB = blk_inlidxs(c, err, thB, listB);
     return;

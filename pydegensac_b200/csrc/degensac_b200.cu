@@ -11,6 +11,7 @@
 // exactly like the reference's x86-64 (no-FMA) build; there is no tensor-core work and no CPU fallback.
 #include <cuda_runtime.h>
 #include <mutex>
+#include <vector>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -63,10 +64,16 @@ int cfg_smem_tile() {
   return v;
 }
 
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 struct BatchArgs {
   const double* x1y1;
   const double* x2y2;
-  int n_pairs, n, dim;
+  const int* offsets;   // ragged batches: pair p owns rows offsets[p] .. offsets[p+1] of the concatenated arrays; nullptr: n each
+  int n_pairs, n, dim;  // n: correspondences per pair (ragged: the largest, which sizes the slabs)
   double px_th, conf, laf_coef;
   int max_iters, metric, sym_check, degen;
   const unsigned long long* seeds;
@@ -79,6 +86,8 @@ struct BatchArgs {
   int* work_counter;
   int pts_in_smem;
   int tile32_in_smem;   // FP32 filter tile placement (F path)
+  int aligned16;        // both input pointers 16-byte aligned: dim == 2 rows are read as double2
+  int filter32;         // FP32 upper-bound filter in the F wave (DGB200_FILTER32=0 scores the wave in FP64; same results)
   const int* ready;     // host-buffer flavour: number of leading pairs whose input has landed in HBM (nullptr: all)
   int* status;          // [0] = 1 once a CTA gave up waiting for its input, [1] = smallest pair index given up on
   long long wait_cycles;   // patience of that wait
@@ -90,21 +99,20 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
   __shared__ int s_pair;
   dg::BlockScratch* sc = reinterpret_cast<dg::BlockScratch*>(smem_raw);
   const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128);
-  const int n = a.n;
   dg::Workspace W;
   double* soa_global;
-  dg::workspace_carve(a.workspace + (size_t)blockIdx.x * a.ws_stride, n, a.chunk, &W, &soa_global);
-  const size_t row = dg::align_up(sizeof(double) * (size_t)n, 128) / sizeof(double);
+  dg::workspace_carve(a.workspace + (size_t)blockIdx.x * a.ws_stride, a.n, a.chunk, &W, &soa_global);
+  const size_t row = dg::align_up(sizeof(double) * (size_t)a.n, 128) / sizeof(double);
   double* soa = a.pts_in_smem ? reinterpret_cast<double*>(smem_raw + sc_bytes) : soa_global;
-  const size_t soa_smem_bytes = a.pts_in_smem ? dg::align_up(sizeof(double) * (size_t)n, 128) * 4 : 0;
+  const size_t soa_smem_bytes = a.pts_in_smem ? dg::align_up(sizeof(double) * (size_t)a.n, 128) * 4 : 0;
   dg::Pt32* tile32 = a.tile32_in_smem
                          ? reinterpret_cast<dg::Pt32*>(smem_raw + sc_bytes + soa_smem_bytes)
-                         : reinterpret_cast<dg::Pt32*>(dg::workspace_tile32(a.workspace + (size_t)blockIdx.x * a.ws_stride, n, a.chunk));
+                         : reinterpret_cast<dg::Pt32*>(dg::workspace_tile32(a.workspace + (size_t)blockIdx.x * a.ws_stride, a.n, a.chunk));
   dg::Tile32 t32;
 
   dg::Ctx c;
   c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5;
-  c.N = n;
+  c.N = a.n;
   c.x1 = soa; c.y1 = soa + row; c.x2 = soa + 2 * row; c.y2 = soa + 3 * row;
   c.sc = sc;
   c.t32 = nullptr;
@@ -138,10 +146,13 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
       __syncthreads();
       if (!s_ok) break;
     }
-    // ---- stage the pair: HBM -> SoA tile
-    const double* g1 = a.x1y1 + (size_t)p * n * a.dim;
-    const double* g2 = a.x2y2 + (size_t)p * n * a.dim;
-    if (a.dim == 2) {
+    // ---- stage the pair: HBM -> SoA tile (the only read of the pair from HBM)
+    const size_t row0 = a.offsets ? (size_t)a.offsets[p] : (size_t)p * a.n;
+    const int n = a.offsets ? a.offsets[p + 1] - a.offsets[p] : a.n;
+    c.N = n;
+    const double* g1 = a.x1y1 + row0 * a.dim;
+    const double* g2 = a.x2y2 + row0 * a.dim;
+    if (a.dim == 2 && a.aligned16) {   // rows are 16 bytes, so every pair of a ragged batch starts aligned too
       const double2* v1 = reinterpret_cast<const double2*>(g1);
       const double2* v2 = reinterpret_cast<const double2*>(g2);
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -152,8 +163,8 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double* q1 = g1 + (size_t)i * a.dim;
         const double* q2 = g2 + (size_t)i * a.dim;
-        soa[i] = q1[0]; soa[row + i] = q1[1];
-        soa[2 * row + i] = q2[0]; soa[3 * row + i] = q2[1];
+        soa[i] = __ldcg(q1); soa[row + i] = __ldcg(q1 + 1);
+        soa[2 * row + i] = __ldcg(q2); soa[3 * row + i] = __ldcg(q2 + 1);
         if (use_laf) {   // columns (x, y, a11, a12, a21, a22): p1 = x + (a12, a22), p2 = x + (a11, a21) (bindings.cpp:355-385)
           W.laf[0][i] = q1[0] + q1[3]; W.laf[1][i] = q1[1] + q1[5]; W.laf[2][i] = q2[0] + q2[3]; W.laf[3][i] = q2[1] + q2[5];
           W.laf[4][i] = q1[0] + q1[2]; W.laf[5][i] = q1[1] + q1[4]; W.laf[6][i] = q2[0] + q2[2]; W.laf[7][i] = q2[1] + q2[4];
@@ -163,12 +174,15 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
     __syncthreads();
     const unsigned long long seed = a.seeds ? a.seeds[p] : (unsigned long long)p;
     double* model = a.model_out + (size_t)p * 9;
-    unsigned char* mask = a.mask_out + (size_t)p * n;
+    unsigned char* mask = a.mask_out + row0;
     int local_stats[4];
     __shared__ int s_stats[4];
     if (KIND == 0) {
-      dg::blk_prepare_tile32(c, tile32, &t32);
-      c.t32 = &t32;
+      c.t32 = nullptr;
+      if (a.filter32) {
+        dg::blk_prepare_tile32(c, tile32, &t32);
+        c.t32 = &t32;
+      }
       dg::FParams P;
       dg::f_thresholds(a.px_th, a.sym_check, &P.th, &P.sym_th);
       P.conf = a.conf; P.laf_coef = a.laf_coef; P.max_iters = a.max_iters; P.metric = a.metric; P.degen = a.degen;
@@ -195,12 +209,21 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
 }
 
 // ------------------------------------------------------------------------------------ host side
+// Device-wide state (created once per device) and a pool of launch contexts: a launch needs its own slab area and
+// work counter, so two calls in flight on different streams never share scratch.  A context is reused by the stream
+// that used it last (stream order serialises the two kernels) or by anybody once its last launch has completed.
+struct LaunchCtx {
+  unsigned char* ws = nullptr; size_t ws_bytes = 0;
+  int* counter = nullptr;
+  cudaEvent_t done = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool used = false;
+};
 struct Cache {
   int device = -1;
   int sm_count = 0;
   size_t smem_optin = 0;
-  unsigned char* ws = nullptr; size_t ws_bytes = 0;
-  int* counter = nullptr;
+  std::vector<LaunchCtx> ctxs;
   unsigned char* io = nullptr; size_t io_bytes = 0;   // staging for the host-buffer flavour
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_feed = nullptr;
   cudaStream_t s_run = nullptr, s_copy = nullptr;     // host-buffer flavour: kernel stream + input feed stream
@@ -210,7 +233,7 @@ struct Cache {
 constexpr int kMaxChunks = 16;
 std::mutex g_mu;
 Cache g_c;
-char g_err[512] = "";
+thread_local char g_err[512] = "";
 long long g_launches = 0;
 double g_last_ms = 0.0;
 
@@ -225,6 +248,24 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     if (e__ != cudaSuccess) return fail(DGB200_E_CUDA, #call, e__);  \
   } while (0)
 
+void destroy_device_state() {   // with the owning device current
+  for (LaunchCtx& x : g_c.ctxs) {
+    if (x.ws) cudaFree(x.ws);
+    if (x.counter) cudaFree(x.counter);
+    if (x.done) cudaEventDestroy(x.done);
+  }
+  g_c.ctxs.clear();
+  if (g_c.io) cudaFree(g_c.io);
+  if (g_c.ready) cudaFree(g_c.ready);
+  if (g_c.h_ready) cudaFreeHost(g_c.h_ready);
+  if (g_c.ev0) cudaEventDestroy(g_c.ev0);
+  if (g_c.ev1) cudaEventDestroy(g_c.ev1);
+  if (g_c.ev_feed) cudaEventDestroy(g_c.ev_feed);
+  if (g_c.s_run) cudaStreamDestroy(g_c.s_run);
+  if (g_c.s_copy) cudaStreamDestroy(g_c.s_copy);
+  g_c = Cache();
+}
+
 int ensure_device() {
   if (g_c.device >= 0) { CU(cudaSetDevice(g_c.device)); return 0; }
   int cnt = 0;
@@ -234,31 +275,76 @@ int ensure_device() {
   cudaGetDevice(&dev);
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, dev));
-  g_c.device = dev;
-  g_c.sm_count = prop.multiProcessorCount;
-  g_c.smem_optin = prop.sharedMemPerBlockOptin;
-  CU(cudaEventCreate(&g_c.ev0));
-  CU(cudaEventCreate(&g_c.ev1));
-  CU(cudaEventCreateWithFlags(&g_c.ev_feed, cudaEventDisableTiming));
-  CU(cudaStreamCreateWithFlags(&g_c.s_run, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&g_c.s_copy, cudaStreamNonBlocking));
-  CU(cudaMalloc(&g_c.ready, 4 * sizeof(int)));
-  CU(cudaHostAlloc(&g_c.h_ready, kMaxChunks * sizeof(int), cudaHostAllocDefault));
+  Cache c;
+  c.sm_count = prop.multiProcessorCount;
+  c.smem_optin = prop.sharedMemPerBlockOptin;
+  cudaError_t err = cudaSuccess;
+  auto step = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+  step(cudaEventCreate(&c.ev0));
+  step(cudaEventCreate(&c.ev1));
+  step(cudaEventCreateWithFlags(&c.ev_feed, cudaEventDisableTiming));
+  step(cudaStreamCreateWithFlags(&c.s_run, cudaStreamNonBlocking));
+  step(cudaStreamCreateWithFlags(&c.s_copy, cudaStreamNonBlocking));
+  step(cudaMalloc(&c.ready, 4 * sizeof(int)));
+  step(cudaHostAlloc(&c.h_ready, kMaxChunks * sizeof(int), cudaHostAllocDefault));
+  if (err != cudaSuccess) {   // nothing half-initialised survives
+    g_c = c; g_c.device = -1;
+    destroy_device_state();
+    return fail(DGB200_E_CUDA, "device state", err);
+  }
+  c.device = dev;
+  g_c = c;
   return 0;
 }
 
+// a launch context whose scratch nobody can still be using on another stream
+int acquire_ctx(cudaStream_t st, size_t need, LaunchCtx** out) {
+  LaunchCtx* pick = nullptr;
+  for (LaunchCtx& x : g_c.ctxs)
+    if (x.used && x.last_stream == st) { pick = &x; break; }
+  if (!pick)
+    for (LaunchCtx& x : g_c.ctxs)
+      if (!x.used || cudaEventQuery(x.done) == cudaSuccess) { pick = &x; break; }
+  if (!pick) {
+    g_c.ctxs.reserve(64);     // pointers handed out stay valid
+    if (g_c.ctxs.size() >= 64) return fail(DGB200_E_CUDA, "too many launches in flight on distinct streams");
+    g_c.ctxs.emplace_back();
+    pick = &g_c.ctxs.back();
+    CU(cudaEventCreateWithFlags(&pick->done, cudaEventDisableTiming));
+    CU(cudaMalloc(&pick->counter, sizeof(int)));
+  }
+  if (need > pick->ws_bytes) {
+    if (pick->ws) {
+      if (pick->used) CU(cudaEventSynchronize(pick->done));   // same-stream reuse with a larger batch: wait before freeing
+      cudaFree(pick->ws);
+    }
+    pick->ws = nullptr; pick->ws_bytes = 0;
+    CU(cudaMalloc(&pick->ws, need));
+    pick->ws_bytes = need;
+  }
+  *out = pick;
+  return 0;
+}
+
+struct Job {
+  const double* d1; const double* d2; const int* d_offsets;
+  int n_pairs, n, dim;
+  double px_th, conf, laf_coef;
+  int max_iters, metric, sym_check, degen;
+  const unsigned long long* d_seeds;
+  double* d_model; unsigned char* d_mask; int* d_stats;
+};
+
 template <int KIND>
-int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, double px_th, double conf, int max_iters,
-           int metric, int sym_check, int degen, const unsigned long long* d_seeds, double* d_model,
-           unsigned char* d_mask, int* d_stats, cudaStream_t st, const int* d_ready = nullptr, int* d_status = nullptr,
-           long long wait_cycles = 0, double laf_coef = 0.0) {
+int launch(const Job& j, cudaStream_t st, const int* d_ready = nullptr, int* d_status = nullptr, long long wait_cycles = 0) {
   BatchArgs a;
   a.ready = d_ready; a.status = d_status; a.wait_cycles = wait_cycles;
-  a.x1y1 = d1; a.x2y2 = d2; a.n_pairs = n_pairs; a.n = n; a.dim = dim;
-  a.px_th = px_th; a.conf = conf; a.laf_coef = laf_coef; a.max_iters = max_iters; a.metric = metric;
-  a.sym_check = sym_check; a.degen = degen; a.seeds = d_seeds;
-  a.model_out = d_model; a.mask_out = d_mask; a.stats_out = d_stats;
+  a.x1y1 = j.d1; a.x2y2 = j.d2; a.offsets = j.d_offsets; a.n_pairs = j.n_pairs; a.n = j.n; a.dim = j.dim;
+  a.px_th = j.px_th; a.conf = j.conf; a.laf_coef = j.laf_coef; a.max_iters = j.max_iters; a.metric = j.metric;
+  a.sym_check = j.sym_check; a.degen = j.degen; a.seeds = j.d_seeds;
+  a.model_out = j.d_model; a.mask_out = j.d_mask; a.stats_out = j.d_stats;
   a.chunk = kChunk;
+  const int n = j.n;
   const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128);
   const size_t tile = dg::align_up(sizeof(double) * (size_t)n, 128) * 4;       // FP64 SoA of the pair
   const size_t tile32 = (KIND == 0 && 16 * (size_t)n <= 65536) ? dg::align_up(16 * (size_t)n, 128) : 0;   // FP32 filter tile
@@ -270,7 +356,9 @@ int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, doub
   size_t smem = sc_bytes;
   a.pts_in_smem = 0;
   a.tile32_in_smem = 0;
-  if (tile32 && smem + tile32 <= g_c.smem_optin) { a.tile32_in_smem = 1; smem += tile32; }
+  a.filter32 = (KIND == 0) ? (env_int("DGB200_FILTER32", 1) != 0) : 0;   // parity switch, read at every launch
+  a.aligned16 = ((((uintptr_t)j.d1) | ((uintptr_t)j.d2)) & 15) == 0 ? 1 : 0;
+  if (tile32 && a.filter32 && smem + tile32 <= g_c.smem_optin) { a.tile32_in_smem = 1; smem += tile32; }
   int per_sm = 0;
   const int want_tile = cfg_smem_tile();
   if (want_tile != 0 && smem + tile <= g_c.smem_optin) {
@@ -285,23 +373,21 @@ int launch(const double* d1, const double* d2, int n_pairs, int n, int dim, doub
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   }
   if (per_sm < 1) return fail(DGB200_E_CUDA, "kernel does not fit on an SM");
-  if (const char* e = getenv("DGB200_CTAS_PER_SM")) { const int cap = atoi(e); if (cap >= 1 && cap < per_sm) per_sm = cap; }
+  { const int cap = env_int("DGB200_CTAS_PER_SM", 0); if (cap >= 1 && cap < per_sm) per_sm = cap; }
   int grid = g_c.sm_count * per_sm;     // persistent CTAs: a whole number of CTAs per SM
-  if (grid > n_pairs) grid = n_pairs;
-  a.ws_stride = dg::align_up(dg::workspace_bytes(n, kChunk), 256);
+  if (grid > j.n_pairs) grid = j.n_pairs;
+  a.ws_stride = dg::align_up(dg::workspace_bytes(n, a.chunk), 256);
   const size_t need = a.ws_stride * (size_t)grid;
-  if (need > g_c.ws_bytes) {
-    if (g_c.ws) cudaFree(g_c.ws);
-    g_c.ws = nullptr; g_c.ws_bytes = 0;
-    CU(cudaMalloc(&g_c.ws, need));
-    g_c.ws_bytes = need;
-  }
-  if (!g_c.counter) CU(cudaMalloc(&g_c.counter, sizeof(int)));
-  a.workspace = g_c.ws;
-  a.work_counter = g_c.counter;
-  CU(cudaMemsetAsync(g_c.counter, 0, sizeof(int), st));
+  LaunchCtx* lc = nullptr;
+  const int rc = acquire_ctx(st, need, &lc);
+  if (rc) return rc;
+  a.workspace = lc->ws;
+  a.work_counter = lc->counter;
+  CU(cudaMemsetAsync(lc->counter, 0, sizeof(int), st));
   kern<<<grid, kThreads, smem, st>>>(a);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(lc->done, st));
+  lc->used = true; lc->last_stream = st;
   ++g_launches;
   return 0;
 }
@@ -318,22 +404,44 @@ int check_args(int kind, const void* p1, const void* p2, int n_pairs, int n, int
   if (laf_coef > 0 && dim != 6) return fail(DGB200_E_ARG, "laf_coef > 0 needs [n,6] inputs (x, y, a11, a12, a21, a22)");
   return 0;
 }
+// ragged batches: offsets[0] = 0, non-decreasing, every pair at least `min_n` rows; returns the largest pair in *n_max
+int check_offsets(int kind, const int32_t* offsets, int n_pairs, int* n_max, long long* total) {
+  if (!offsets) return fail(DGB200_E_ARG, "null offsets");
+  if (offsets[0] != 0) return fail(DGB200_E_ARG, "offsets[0] must be 0");
+  int mx = 0;
+  const int min_n = kind == 0 ? 8 : 4;
+  for (int p = 0; p < n_pairs; ++p) {
+    const long long n = (long long)offsets[p + 1] - offsets[p];
+    if (n < min_n) return fail(DGB200_E_ARG, kind == 0 ? "every pair needs n >= 8 correspondences" : "every pair needs n >= 4 correspondences");
+    if (n > mx) mx = (int)n;
+  }
+  *n_max = mx;
+  *total = offsets[n_pairs];
+  return 0;
+}
 
 template <int KIND>
-int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim, double px_th, double conf,
-             int max_iters, int metric, int sym_check, double laf_coef, int degen, const uint64_t* seeds,
+int run_host(const double* x1y1, const double* x2y2, const int32_t* offsets, int n_pairs, int n, int dim, double px_th,
+             double conf, int max_iters, int metric, int sym_check, double laf_coef, int degen, const uint64_t* seeds,
              double* model_out, uint8_t* mask_out, int32_t* stats_out) {
   std::lock_guard<std::mutex> lk(g_mu);
+  long long rows = (long long)n_pairs * n;
+  if (offsets) {
+    if (n_pairs < 1) return fail(DGB200_E_ARG, "n_pairs must be >= 1");
+    const int rc0 = check_offsets(KIND, offsets, n_pairs, &n, &rows);
+    if (rc0) return rc0;
+  }
   int rc = check_args(KIND, x1y1, x2y2, n_pairs, n, dim, metric, laf_coef, model_out, mask_out);
   if (rc) return rc;
   rc = ensure_device();
   if (rc) return rc;
-  const size_t in_b = dg::align_up(sizeof(double) * (size_t)n_pairs * n * dim, 256);
+  const size_t in_b = dg::align_up(sizeof(double) * (size_t)rows * dim, 256);
   const size_t seed_b = dg::align_up(sizeof(uint64_t) * (size_t)n_pairs, 256);
+  const size_t off_b = dg::align_up(sizeof(int32_t) * ((size_t)n_pairs + 1), 256);
   const size_t model_b = dg::align_up(sizeof(double) * 9 * (size_t)n_pairs, 256);
-  const size_t mask_b = dg::align_up((size_t)n_pairs * n, 256);
+  const size_t mask_b = dg::align_up((size_t)rows, 256);
   const size_t stats_b = dg::align_up(sizeof(int) * 4 * (size_t)n_pairs, 256);
-  const size_t need = 2 * in_b + seed_b + model_b + mask_b + stats_b;
+  const size_t need = 2 * in_b + seed_b + off_b + model_b + mask_b + stats_b;
   if (need > g_c.io_bytes) {
     if (g_c.io) cudaFree(g_c.io);
     g_c.io = nullptr; g_c.io_bytes = 0;
@@ -344,16 +452,21 @@ int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim
   double* d1 = (double*)p; p += in_b;
   double* d2 = (double*)p; p += in_b;
   unsigned long long* dseed = (unsigned long long*)p; p += seed_b;
+  int* doff = (int*)p; p += off_b;
   double* dmodel = (double*)p; p += model_b;
   unsigned char* dmask = p; p += mask_b;
   int* dstats = (int*)p;
+  Job j;
+  j.d1 = d1; j.d2 = d2; j.d_offsets = offsets ? doff : nullptr; j.n_pairs = n_pairs; j.n = n; j.dim = dim;
+  j.px_th = px_th; j.conf = conf; j.laf_coef = laf_coef; j.max_iters = max_iters; j.metric = metric;
+  j.sym_check = sym_check; j.degen = degen; j.d_seeds = seeds ? dseed : nullptr;
+  j.d_model = dmodel; j.d_mask = dmask; j.d_stats = dstats;
   // Input feed overlapped with the kernel: the batch is copied in chunks on a copy stream; after every chunk the
   // device-side `ready` count is bumped (a 4-byte copy from pinned memory, ordered behind the chunk) and the
-  // persistent CTAs wait on it before staging a pair.  Chunk 0 covers at least two pairs per CTA.
+  // persistent CTAs wait on it before staging a pair.  Chunk 0 covers the pairs the CTAs start with.
   cudaStream_t st = g_c.s_run, cs = g_c.s_copy;
-  const size_t pair_elems = (size_t)n * dim;
   int nchunks = 8;
-  int first = 2 * 2 * g_c.sm_count;
+  int first = 2 * DG_LB_BLOCKS * g_c.sm_count;   // two pairs per resident CTA
   if (first > n_pairs) first = n_pairs;
   int rest = n_pairs - first;
   if (rest <= 0) nchunks = 1;
@@ -361,24 +474,26 @@ int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim
   static const int k_init[4] = {0, 0, 0x7fffffff, 0};      // ready, abort flag, first pair given up on
   CU(cudaMemcpyAsync(g_c.ready, k_init, sizeof(k_init), cudaMemcpyHostToDevice, cs));
   // patience of a waiting CTA: the whole input at a pessimistic 4 GB/s plus 20 ms, in SM cycles (<= 2.1 GHz)
-  const double feed_s = 2.0 * sizeof(double) * (double)n_pairs * (double)pair_elems / 4e9 + 0.020;
+  const double feed_s = 2.0 * sizeof(double) * (double)rows * (double)dim / 4e9 + 0.020;
   long long wait_cycles = (long long)(feed_s * 2.1e9);
   if (const char* e = getenv("DGB200_FEED_WAIT_US")) wait_cycles = (long long)(atof(e) * 2.1e3);   // tests: force the fallback
   if (seeds) CU(cudaMemcpyAsync(dseed, seeds, sizeof(uint64_t) * (size_t)n_pairs, cudaMemcpyHostToDevice, cs));
+  if (offsets) CU(cudaMemcpyAsync(doff, offsets, sizeof(int32_t) * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, cs));
   CU(cudaEventRecord(g_c.ev_feed, cs));
   CU(cudaStreamWaitEvent(st, g_c.ev_feed, 0));
   CU(cudaEventRecord(g_c.ev0, st));
-  rc = launch<KIND>(d1, d2, n_pairs, n, dim, px_th, conf, max_iters, metric, sym_check, degen, seeds ? dseed : nullptr,
-                    dmodel, dmask, dstats, st, g_c.ready, g_c.ready + 1, wait_cycles, laf_coef);
+  rc = launch<KIND>(j, st, g_c.ready, g_c.ready + 1, wait_cycles);
   if (rc) return rc;
   CU(cudaEventRecord(g_c.ev1, st));
+  auto row_of = [&](int pair) -> size_t { return offsets ? (size_t)offsets[pair] : (size_t)pair * n; };
   int done = 0;
   for (int ci = 0; ci < nchunks && done < n_pairs; ++ci) {
     int cnt = (ci == 0) ? first : per;
     if (done + cnt > n_pairs) cnt = n_pairs - done;
-    const size_t off = (size_t)done * pair_elems;
-    const cudaError_t e1 = cudaMemcpyAsync(d1 + off, x1y1 + off, sizeof(double) * (size_t)cnt * pair_elems, cudaMemcpyHostToDevice, cs);
-    const cudaError_t e2 = cudaMemcpyAsync(d2 + off, x2y2 + off, sizeof(double) * (size_t)cnt * pair_elems, cudaMemcpyHostToDevice, cs);
+    const size_t off = row_of(done) * dim;
+    const size_t elems = (row_of(done + cnt) - row_of(done)) * dim;
+    const cudaError_t e1 = cudaMemcpyAsync(d1 + off, x1y1 + off, sizeof(double) * elems, cudaMemcpyHostToDevice, cs);
+    const cudaError_t e2 = cudaMemcpyAsync(d2 + off, x2y2 + off, sizeof(double) * elems, cudaMemcpyHostToDevice, cs);
     done += cnt;
     g_c.h_ready[ci] = (e1 == cudaSuccess && e2 == cudaSuccess) ? done : n_pairs + 1;   // on a failed copy release the CTAs anyway
     cudaMemcpyAsync(g_c.ready, &g_c.h_ready[ci], sizeof(int), cudaMemcpyHostToDevice, cs);
@@ -392,20 +507,33 @@ int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim
   CU(cudaStreamSynchronize(cs));
   CU(cudaStreamSynchronize(st));
   if (h_status[1] != 0) {
-    // the feed could not overlap the kernel: everything has landed by now, finish the remaining pairs normally
+    // The feed could not overlap the kernel and some CTAs stopped taking pairs.  Everything has landed by now: run
+    // the pairs from the first abandoned index on in an ordinary launch (pairs before it were completed -- a CTA only
+    // abandons the pair it was about to START; pairs it had in flight are finished before it exits).
     int from = h_status[2];
     if (from < 0) from = 0;
     if (from < n_pairs) {
-      const size_t off = (size_t)from * pair_elems;
-      rc = launch<KIND>(d1 + off, d2 + off, n_pairs - from, n, dim, px_th, conf, max_iters, metric, sym_check, degen,
-                        seeds ? dseed + from : nullptr, dmodel + (size_t)9 * from, dmask + (size_t)from * n,
-                        dstats + (size_t)4 * from, st, nullptr, nullptr, 0, laf_coef);
+      Job r = j;
+      r.n_pairs = n_pairs - from;
+      r.d_seeds = seeds ? dseed + from : nullptr;
+      r.d_model = dmodel + (size_t)9 * from;
+      r.d_stats = dstats + (size_t)4 * from;
+      if (offsets) {
+        // ragged: re-base the offsets of the remaining pairs (host copy, tiny)
+        std::vector<int32_t> rebased((size_t)r.n_pairs + 1);
+        for (int q = 0; q <= r.n_pairs; ++q) rebased[q] = offsets[from + q] - offsets[from];
+        CU(cudaMemcpyAsync(doff, rebased.data(), sizeof(int32_t) * rebased.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+      }
+      const size_t off = row_of(from);
+      r.d1 = d1 + off * dim; r.d2 = d2 + off * dim; r.d_mask = dmask + off;
+      rc = launch<KIND>(r, st);
       if (rc) return rc;
       CU(cudaEventRecord(g_c.ev1, st));
     }
   }
   CU(cudaMemcpyAsync(model_out, dmodel, sizeof(double) * 9 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(mask_out, dmask, (size_t)n_pairs * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(mask_out, dmask, (size_t)rows, cudaMemcpyDeviceToHost, st));
   if (stats_out) CU(cudaMemcpyAsync(stats_out, dstats, sizeof(int) * 4 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   float ms = 0.f;
@@ -415,17 +543,20 @@ int run_host(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim
 }
 
 template <int KIND>
-int run_dev(const double* d1, const double* d2, int n_pairs, int n, int dim, double px_th, double conf, int max_iters,
-            int metric, int sym_check, double laf_coef, int degen, const uint64_t* d_seeds, double* d_model,
-            uint8_t* d_mask, int32_t* d_stats, void* stream) {
+int run_dev(const double* d1, const double* d2, const int32_t* d_offsets, int n_pairs, int n, int dim, double px_th,
+            double conf, int max_iters, int metric, int sym_check, double laf_coef, int degen, const uint64_t* d_seeds,
+            double* d_model, uint8_t* d_mask, int32_t* d_stats, void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   int rc = check_args(KIND, d1, d2, n_pairs, n, dim, metric, laf_coef, d_model, d_mask);
   if (rc) return rc;
   rc = ensure_device();
   if (rc) return rc;
-  return launch<KIND>(d1, d2, n_pairs, n, dim, px_th, conf, max_iters, metric, sym_check, degen,
-                      (const unsigned long long*)d_seeds, d_model, d_mask, d_stats, (cudaStream_t)stream, nullptr, nullptr, 0,
-                      laf_coef);
+  Job j;
+  j.d1 = d1; j.d2 = d2; j.d_offsets = d_offsets; j.n_pairs = n_pairs; j.n = n; j.dim = dim;
+  j.px_th = px_th; j.conf = conf; j.laf_coef = laf_coef; j.max_iters = max_iters; j.metric = metric;
+  j.sym_check = sym_check; j.degen = degen; j.d_seeds = (const unsigned long long*)d_seeds;
+  j.d_model = d_model; j.d_mask = d_mask; j.d_stats = d_stats;
+  return launch<KIND>(j, (cudaStream_t)stream);
 }
 
 }  // namespace
@@ -436,43 +567,73 @@ int dgb200_find_fundamental_batch(const double* x1y1, const double* x2y2, int n_
                                   double conf, int max_iters, int error_type, int sym_check, double laf_coef,
                                   int degen_check, const uint64_t* seeds, double* F_out, uint8_t* mask_out,
                                   int32_t* stats_out) {
-  return run_host<0>(x1y1, x2y2, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check,
-                     seeds, F_out, mask_out, stats_out);
+  return run_host<0>(x1y1, x2y2, nullptr, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef,
+                     degen_check, seeds, F_out, mask_out, stats_out);
 }
 int dgb200_find_homography_batch(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim, double px_th,
                                  double conf, int max_iters, int error_type, int sym_check, double laf_coef,
                                  const uint64_t* seeds, double* H_out, uint8_t* mask_out, int32_t* stats_out) {
-  return run_host<1>(x1y1, x2y2, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0, seeds,
-                     H_out, mask_out, stats_out);
+  return run_host<1>(x1y1, x2y2, nullptr, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0,
+                     seeds, H_out, mask_out, stats_out);
+}
+int dgb200_find_fundamental_ragged(const double* x1y1, const double* x2y2, const int32_t* offsets, int n_pairs, int dim,
+                                   double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                   double laf_coef, int degen_check, const uint64_t* seeds, double* F_out,
+                                   uint8_t* mask_out, int32_t* stats_out) {
+  return run_host<0>(x1y1, x2y2, offsets, n_pairs, 0, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef,
+                     degen_check, seeds, F_out, mask_out, stats_out);
+}
+int dgb200_find_homography_ragged(const double* x1y1, const double* x2y2, const int32_t* offsets, int n_pairs, int dim,
+                                  double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                  double laf_coef, const uint64_t* seeds, double* H_out, uint8_t* mask_out,
+                                  int32_t* stats_out) {
+  return run_host<1>(x1y1, x2y2, offsets, n_pairs, 0, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0,
+                     seeds, H_out, mask_out, stats_out);
 }
 int dgb200_find_fundamental_batch_dev(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
                                       double px_th, double conf, int max_iters, int error_type, int sym_check,
                                       double laf_coef, int degen_check, const uint64_t* d_seeds, double* d_F_out,
                                       uint8_t* d_mask_out, int32_t* d_stats_out, void* stream) {
-  return run_dev<0>(d_x1y1, d_x2y2, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef,
+  return run_dev<0>(d_x1y1, d_x2y2, nullptr, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef,
                     degen_check, d_seeds, d_F_out, d_mask_out, d_stats_out, stream);
 }
 int dgb200_find_homography_batch_dev(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
                                      double px_th, double conf, int max_iters, int error_type, int sym_check,
                                      double laf_coef, const uint64_t* d_seeds, double* d_H_out, uint8_t* d_mask_out,
                                      int32_t* d_stats_out, void* stream) {
-  return run_dev<1>(d_x1y1, d_x2y2, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0,
+  return run_dev<1>(d_x1y1, d_x2y2, nullptr, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0,
                     d_seeds, d_H_out, d_mask_out, d_stats_out, stream);
+}
+int dgb200_find_fundamental_ragged_dev(const double* d_x1y1, const double* d_x2y2, const int32_t* d_offsets, int n_pairs,
+                                       int n_max, int dim, double px_th, double conf, int max_iters, int error_type,
+                                       int sym_check, double laf_coef, int degen_check, const uint64_t* d_seeds,
+                                       double* d_F_out, uint8_t* d_mask_out, int32_t* d_stats_out, void* stream) {
+  if (!d_offsets) return fail(DGB200_E_ARG, "null offsets");
+  return run_dev<0>(d_x1y1, d_x2y2, d_offsets, n_pairs, n_max, dim, px_th, conf, max_iters, error_type, sym_check,
+                    laf_coef, degen_check, d_seeds, d_F_out, d_mask_out, d_stats_out, stream);
+}
+int dgb200_find_homography_ragged_dev(const double* d_x1y1, const double* d_x2y2, const int32_t* d_offsets, int n_pairs,
+                                      int n_max, int dim, double px_th, double conf, int max_iters, int error_type,
+                                      int sym_check, double laf_coef, const uint64_t* d_seeds, double* d_H_out,
+                                      uint8_t* d_mask_out, int32_t* d_stats_out, void* stream) {
+  if (!d_offsets) return fail(DGB200_E_ARG, "null offsets");
+  return run_dev<1>(d_x1y1, d_x2y2, d_offsets, n_pairs, n_max, dim, px_th, conf, max_iters, error_type, sym_check,
+                    laf_coef, 0, d_seeds, d_H_out, d_mask_out, d_stats_out, stream);
 }
 int dgb200_find_fundamental(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
                             int max_iters, int error_type, int sym_check, double laf_coef, int degen_check,
                             uint64_t seed, double* F_out, uint8_t* mask_out, int32_t* stats_out) {
-  return run_host<0>(x1y1, x2y2, 1, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check, &seed,
-                     F_out, mask_out, stats_out);
+  return run_host<0>(x1y1, x2y2, nullptr, 1, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check,
+                     &seed, F_out, mask_out, stats_out);
 }
 int dgb200_find_homography(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
                            int max_iters, int error_type, int sym_check, double laf_coef, uint64_t seed, double* H_out,
                            uint8_t* mask_out, int32_t* stats_out) {
-  return run_host<1>(x1y1, x2y2, 1, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0, &seed, H_out,
-                     mask_out, stats_out);
+  return run_host<1>(x1y1, x2y2, nullptr, 1, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0, &seed,
+                     H_out, mask_out, stats_out);
 }
 
-int dgb200_version(void) { return 1; }
+int dgb200_version(void) { return 2; }
 int dgb200_device_count(void) {
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) != cudaSuccess) return -1;
@@ -481,10 +642,9 @@ int dgb200_device_count(void) {
 int dgb200_set_device(int device) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_c.device >= 0 && g_c.device != device) {
-    if (g_c.ws) cudaFree(g_c.ws);
-    if (g_c.io) cudaFree(g_c.io);
-    if (g_c.counter) cudaFree(g_c.counter);
-    g_c = Cache();
+    cudaSetDevice(g_c.device);      // free the old device's state with that device current
+    cudaDeviceSynchronize();
+    destroy_device_state();
   }
   CU(cudaSetDevice(device));
   return 0;
@@ -500,11 +660,15 @@ void dgb200_prof_read(unsigned long long* out, int reset) {
 #endif
 void dgb200_release(void) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_c.device >= 0) cudaSetDevice(g_c.device);
-  if (g_c.ws) cudaFree(g_c.ws);
+  if (g_c.device < 0) return;
+  cudaSetDevice(g_c.device);
+  cudaDeviceSynchronize();
+  for (LaunchCtx& x : g_c.ctxs) {
+    if (x.ws) cudaFree(x.ws);
+    x.ws = nullptr; x.ws_bytes = 0;
+  }
   if (g_c.io) cudaFree(g_c.io);
-  if (g_c.counter) cudaFree(g_c.counter);
-  g_c.ws = nullptr; g_c.io = nullptr; g_c.counter = nullptr; g_c.ws_bytes = 0; g_c.io_bytes = 0;
+  g_c.io = nullptr; g_c.io_bytes = 0;
 }
 
 }  // extern "C"

@@ -161,6 +161,11 @@ def _batch_seeds(seeds, P):
     return seeds
 
 
+def _is_ragged(pts):
+    """A list/tuple of per-pair arrays (possibly of different lengths) rather than one [P,N,dim] array."""
+    return isinstance(pts, (list, tuple)) and len(pts) > 0 and np.ndim(pts[0]) == 2
+
+
 def _batch_laf(coef, p1):
     """The single-pair API's treatment of laf_consistensy_coef (utils.py:87-89, 116): dropped with a warning for
     (x, y)-only keypoints, clamped at 0."""
@@ -174,9 +179,16 @@ def findFundamentalMatrixBatch(pts1, pts2, px_th=0.5, conf=0.9999, max_iters=100
                                symmetric_error_check=True, enable_degeneracy_check=True, seeds=None,
                                return_stats=False, laf_consistensy_coef=-1.0):
     """Batched findFundamentalMatrix over P independent pairs: pts [P,N,2] (or [P,N,6] with local affine shapes)
-    -> (F [P,3,3], mask [P,N] bool).  Pairs without a model get an all-zero F and an all-False mask row."""
+    -> (F [P,3,3], mask [P,N] bool).  Pairs without a model get an all-zero F and an all-False mask row.
+    RAGGED batches: pass two lists of [n_i, 2] (or [n_i, 6]) arrays -> (F [P,3,3], list of P bool masks); one kernel
+    launch, same results as one call per pair with the same seed."""
     from . import _cabi
     et = _error_type(error_type, error_type_dict_fundamental)
+    if _is_ragged(pts1):
+        F, masks, stats = _cabi.fundamental_ragged(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check,
+                                                   _batch_laf(laf_consistensy_coef, np.asarray(pts1[0])),
+                                                   enable_degeneracy_check, _batch_seeds(seeds, len(pts1)))
+        return (F, masks, stats) if return_stats else (F, masks)
     p1 = np.asarray(pts1)
     F, mask, stats = _cabi.fundamental_batch(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check,
                                              _batch_laf(laf_consistensy_coef, p1),
@@ -186,9 +198,19 @@ def findFundamentalMatrixBatch(pts1, pts2, px_th=0.5, conf=0.9999, max_iters=100
 
 def findHomographyBatch(pts1, pts2, px_th=1.0, conf=0.999, max_iters=50000, error_type="sampson",
                         symmetric_error_check=True, seeds=None, return_stats=False, laf_consistensy_coef=-1.0):
-    """Batched findHomography: pts [P,N,2] (or [P,N,6]) -> (H [P,3,3] OpenCV convention, mask [P,N] bool)."""
+    """Batched findHomography: pts [P,N,2] (or [P,N,6]) -> (H [P,3,3] OpenCV convention, mask [P,N] bool).
+    RAGGED batches: two lists of [n_i, 2] (or [n_i, 6]) arrays -> (H [P,3,3], list of P bool masks)."""
     from . import _cabi
     et = _error_type(error_type, error_type_dict_homography)
+    if _is_ragged(pts1):
+        Hraw, masks, stats = _cabi.homography_ragged(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check,
+                                                     _batch_laf(laf_consistensy_coef, np.asarray(pts1[0])),
+                                                     _batch_seeds(seeds, len(pts1)))
+        H = np.zeros_like(Hraw)
+        for i in range(Hraw.shape[0]):
+            if np.abs(Hraw[i]).sum() != 0:
+                H[i] = np.linalg.inv(Hraw[i].T)
+        return (H, masks, stats) if return_stats else (H, masks)
     p1 = np.asarray(pts1)
     Hraw, mask, stats = _cabi.homography_batch(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check,
                                                _batch_laf(laf_consistensy_coef, p1), _batch_seeds(seeds, p1.shape[0]))

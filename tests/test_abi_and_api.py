@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 12
     for s in syms:
         assert hasattr(lib, s), "missing export " + s
-    assert lib.dgb200_version() == 1
+    assert lib.dgb200_version() == 2
 
 
 def test_argument_errors_before_any_cuda_call():

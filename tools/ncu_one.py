@@ -4,6 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from pydegensac_b200 import _cabi
+if os.environ.get('DGLIB'): _cabi._LIBPATH = os.path.abspath(os.environ['DGLIB'])
 from pydegensac_b200.scenes import batch_F
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 N = 2000
