@@ -160,10 +160,28 @@ DG_ENG inline void blk_scan_sum(const Ctx& c, int cnt, double J, int* off, int* 
 DG_ENG inline double ld_row(const double* p) { return __ldcg(p); }
 DG_ENG inline void st_row(double* p, double v) { __stcg(p, v); }
 DG_ENG inline void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// correspondences read by the streaming O(N) passes (every residual row reads all four SoA rows once): DG_SOA_LD = 1
+// keeps them from allocating in L1, 2 = L2 only (ld.cg; measured best: +5 %, the L1 lines the serial steps live on --
+// stack, lists, hypothesis queue -- are no longer swept out by every residual row), 0 = default caching
+#ifndef DG_SOA_LD
+#define DG_SOA_LD 2
+#endif
+DG_ENG inline double ld_soa(const double* p) {
+#if DG_SOA_LD == 1
+  double v;
+  asm("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#elif DG_SOA_LD == 2
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
 #else
 inline double ld_row(const double* p) { return *p; }
 inline void st_row(double* p, double v) { *p = v; }
 inline void prefetch_l1(const void*) {}
+inline double ld_soa(const double* p) { return *p; }
 #endif
 
 

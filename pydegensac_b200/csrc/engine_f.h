@@ -397,26 +397,31 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
         FFilter32 ff;
         f_filter_setup(P.metric, f, *c.t32, w94, &ff);
         float J = 0.0f;
-        const Pt32* pts = c.t32->pts;
 #if DG_DEVICE_PASS
-        {  // four independent gain chains per lane (sqrt + divide each): the loop is latency-, not issue-bound
-          float J1 = 0.0f, J2 = 0.0f, J3 = 0.0f;
+        {  // packed pairs (FFMA2), two independent pair chains per lane and trip
+          FFilter32x2 f2;
+          f_filter_pack(ff, &f2);
+          const float4* tp = reinterpret_cast<const float4*>(c.t32->pts);
+          const int npair = (c.N + 1) >> 1;
+          const int last = (c.N & 1) ? npair - 1 : -1;     // pair whose second slot is padding
+          f32x2 Ja = pk2(0.0f, 0.0f), Jb = pk2(0.0f, 0.0f);
           int i = c.lane;
           #pragma unroll 1
-          for (; i + 96 < c.N; i += 128) {
-            const Pt32 p0 = pts[i], p1 = pts[i + 32], p2 = pts[i + 64], p3 = pts[i + 96];
-            J += f_filter_gain(ff, p0); J1 += f_filter_gain(ff, p1); J2 += f_filter_gain(ff, p2); J3 += f_filter_gain(ff, p3);
+          for (; i + 32 < npair; i += 64) {
+            const float4 A0 = tp[2 * i], B0 = tp[2 * i + 1], A1 = tp[2 * i + 64], B1 = tp[2 * i + 65];
+            Ja = add2(Ja, f_filter_gain2(f2, A0, B0, i != last));
+            Jb = add2(Jb, f_filter_gain2(f2, A1, B1, i + 32 != last));
           }
-          #pragma unroll 1
-          for (; i < c.N; i += 32) J += f_filter_gain(ff, pts[i]);
-          J = (J + J1) + (J2 + J3);
+          if (i < npair) Ja = add2(Ja, f_filter_gain2(f2, tp[2 * i], tp[2 * i + 1], i != last));
+          float j0, j1;
+          upk2(add2(Ja, Jb), j0, j1);
+          J = j0 + j1;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) J += __shfl_xor_sync(0xffffffffu, J, o);
         }
 #else
+        const Pt32* pts = c.t32->pts;
         for (int i = 0; i < c.N; ++i) J += f_filter_gain(ff, pts[i]);
-#endif
-#if DG_DEVICE_PASS
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) J += __shfl_xor_sync(0xffffffffu, J, o);
 #endif
         const double Jup = (double)J * (1.0 + 1.52587890625e-05) + 1e-3;
 #ifdef DG_FILTER_CHECK

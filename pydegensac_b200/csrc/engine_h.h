@@ -35,8 +35,8 @@ DG_ENGN void blk_resid_H(const Ctx& c, int metric, const double* h, double* out)
     const int j = i + c.nt;
     const bool two = j < c.N;
     const int jj = two ? j : i;
-    const double e0 = h_resid_metric(metric, h, s, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
-    const double e1 = h_resid_metric(metric, h, s, c.x1[jj], c.y1[jj], c.x2[jj], c.y2[jj]);
+    const double e0 = h_resid_metric(metric, h, s, ld_soa(c.x1 + i), ld_soa(c.y1 + i), ld_soa(c.x2 + i), ld_soa(c.y2 + i));
+    const double e1 = h_resid_metric(metric, h, s, ld_soa(c.x1 + jj), ld_soa(c.y1 + jj), ld_soa(c.x2 + jj), ld_soa(c.y2 + jj));
     st_row(out + i, e0);
     if (two) st_row(out + j, e1);
   }

@@ -58,8 +58,8 @@ DG_ENGN void blk_resid_F(const Ctx& c, int metric, const double* F, double* out)
     const int j = i + c.nt;
     const bool two = j < c.N;
     const int jj = two ? j : i;
-    const double a1 = c.x1[i], b1 = c.y1[i], a2 = c.x2[i], b2 = c.y2[i];
-    const double p1 = c.x1[jj], q1 = c.y1[jj], p2 = c.x2[jj], q2 = c.y2[jj];
+    const double a1 = ld_soa(c.x1 + i), b1 = ld_soa(c.y1 + i), a2 = ld_soa(c.x2 + i), b2 = ld_soa(c.y2 + i);
+    const double p1 = ld_soa(c.x1 + jj), q1 = ld_soa(c.y1 + jj), p2 = ld_soa(c.x2 + jj), q2 = ld_soa(c.y2 + jj);
     const double e0 = f_resid(metric, F, a1, b1, a2, b2);
     const double e1 = f_resid(metric, F, p1, q1, p2, q2);
     st_row(out + i, e0);
@@ -76,8 +76,8 @@ DG_ENGN void blk_resid_w_F(const Ctx& c, int metric, const double* F, double* ou
     const int j = i + c.nt;
     const bool two = j < c.N;
     const int jj = two ? j : i;
-    const double a1 = c.x1[i], b1 = c.y1[i], a2 = c.x2[i], b2 = c.y2[i];
-    const double p1 = c.x1[jj], q1 = c.y1[jj], p2 = c.x2[jj], q2 = c.y2[jj];
+    const double a1 = ld_soa(c.x1 + i), b1 = ld_soa(c.y1 + i), a2 = ld_soa(c.x2 + i), b2 = ld_soa(c.y2 + i);
+    const double p1 = ld_soa(c.x1 + jj), q1 = ld_soa(c.y1 + jj), p2 = ld_soa(c.x2 + jj), q2 = ld_soa(c.y2 + jj);
     double e0, w0, e1, w1;
     f_resid_w(metric, F, a1, b1, a2, b2, &e0, &w0);
     f_resid_w(metric, F, p1, q1, p2, q2, &e1, &w1);

@@ -188,7 +188,7 @@ DG_ENGN void blk_fit_H(const Ctx& c, const int* idx, int len, double* h) {
 
 // Sampson residual row of all correspondences under h (reference HDs over lin_hg, as dHDs does).
 DG_ENGN void blk_resid_H_sampson(const Ctx& c, const double* h, double* out) {
-  for (int i = c.tid; i < c.N; i += c.nt) st_row(out + i, h_resid_sampson(h, c.x1[i], c.y1[i], c.x2[i], c.y2[i]));
+  for (int i = c.tid; i < c.N; i += c.nt) st_row(out + i, h_resid_sampson(h, ld_soa(c.x1 + i), ld_soa(c.y1 + i), ld_soa(c.x2 + i), ld_soa(c.y2 + i)));
   DG_SYNC();
 }
 
