@@ -78,6 +78,29 @@ int dgb200_find_homography_batch_dev(const double* d_x1y1, const double* d_x2y2,
                                      double laf_coef, const uint64_t* d_seeds,
                                      double* d_H_out, uint8_t* d_mask_out, int32_t* d_stats_out, void* stream);
 
+/* Flagged variants.  DGB200_FLAG_FINAL_LSQ = the reference's compile-time option __FINAL_LSQ__ (exp_ranF.h:28-29;
+ * exp_ranF.c:1701-1705, exp_ranH.c:866-870): after the loop one more least-squares fit on all inliers of the best
+ * model, the inlier mask is derived from the polished model's residuals. */
+#define DGB200_FLAG_FINAL_LSQ 1u
+int dgb200_find_fundamental_batch_ex(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim,
+                                     double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                     double laf_coef, int degen_check, const uint64_t* seeds,
+                                     double* F_out, uint8_t* mask_out, int32_t* stats_out, unsigned flags);
+int dgb200_find_homography_batch_ex(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim,
+                                    double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                    double laf_coef, const uint64_t* seeds,
+                                    double* H_out, uint8_t* mask_out, int32_t* stats_out, unsigned flags);
+int dgb200_find_fundamental_batch_dev_ex(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
+                                         double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                         double laf_coef, int degen_check, const uint64_t* d_seeds,
+                                         double* d_F_out, uint8_t* d_mask_out, int32_t* d_stats_out, void* stream,
+                                         unsigned flags);
+int dgb200_find_homography_batch_dev_ex(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
+                                        double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                        double laf_coef, const uint64_t* d_seeds,
+                                        double* d_H_out, uint8_t* d_mask_out, int32_t* d_stats_out, void* stream,
+                                        unsigned flags);
+
 /* Ragged batches (proposal 3): real tentative sets never share n.  The correspondences of all
  * pairs are concatenated ([offsets[n_pairs]][dim] float64); pair p owns rows offsets[p] .. offsets[p+1]-1
  * (offsets[0] = 0, int32, every pair n >= 8 for F / n >= 4 for H); mask_out is concatenated the same way
@@ -109,6 +132,32 @@ int dgb200_find_fundamental(const double* x1y1, const double* x2y2, int n, int d
 int dgb200_find_homography(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
                            int max_iters, int error_type, int sym_check, double laf_coef,
                            uint64_t seed, double* H_out, uint8_t* mask_out, int32_t* stats_out);
+
+/* ---- the steps either side of the path, device-resident, asynchronous on `stream` ----
+ *
+ * Descriptor matching: replaces the host side of the reference's pipeline, cv2.BFMatcher().knnMatch(descs1, descs2, k=2)
+ * + SNN ratio test `m.distance < ratio * n.distance` (examples/simple-example.py:46-53), optionally with a mutual
+ * nearest-neighbour check.  d_desc1 [n1][D], d_desc2 [n2][D] float32 (D a multiple of 4, <= 256); accepted matches in
+ * ascending query order: d_match_q/d_match_t [capacity] int32, *d_count; when d_x1y1 != NULL the first `out_dim`
+ * columns of the keypoint rows d_kp1 [n1][kp_dim], d_kp2 [n2][kp_dim] (float64) are gathered into d_x1y1/d_x2y2
+ * [capacity][out_dim] -- exactly the arrays dgb200_find_*_batch_dev take.  d_workspace: dgb200_match_workspace_bytes(). */
+size_t dgb200_match_workspace_bytes(int n1, int n2);
+int dgb200_match_descriptors_dev(const float* d_desc1, int n1, const float* d_desc2, int n2, int D, float ratio, int mutual,
+                                 const double* d_kp1, const double* d_kp2, int kp_dim, int* d_match_q, int* d_match_t,
+                                 double* d_x1y1, double* d_x2y2, int out_dim, int capacity, int* d_count, void* d_workspace,
+                                 void* stream);
+/* Pose from fundamental matrices: E = K2^T F K1, the four (R, t) candidates of its SVD, cheirality vote over the
+ * correspondences with mask != 0 (NULL: all).  d_K1/d_K2: one 3x3 (k_per_pair = 0) or one per pair, row-major.
+ * Outputs R [n_pairs][9] row-major, t [n_pairs][3] (unit length, x2 ~ R x1 + t), good [n_pairs] = supporters or NULL.
+ * (The reference stops at F; this is the survey's "step after".) */
+int dgb200_pose_from_fundamental_batch_dev(const double* d_F, const double* d_K1, const double* d_K2, int k_per_pair,
+                                           const double* d_x1y1, const double* d_x2y2, const uint8_t* d_mask, int n_pairs,
+                                           int n, int dim, double* d_R_out, double* d_t_out, int32_t* d_good_out,
+                                           void* stream);
+/* The reference's alternative 7-point null-space solver nullspace_qr7x9 (Ftools.c:594-668, compile-time USE_QR,
+ * exp_ranF.c:1346-1349) over `count` systems: d_A [count][7*9] row-major -> d_N [count][2*9], d_rc [count] or NULL. */
+int dgb200_nullspace_qr7x9_batch_dev(const double* d_A, double* d_N, int32_t* d_rc, int count, void* stream);
+const char* dgb200_frontend_last_error(void);
 
 /* Housekeeping */
 int dgb200_version(void);              /* ABI version */

@@ -26,10 +26,17 @@ done
 for f in DegUtils exp_ranF exp_ranH Ftools hash Htools ranF ranH2el ranH rtools utools lapwrap; do
   gcc $CFLAGS -c "$SRC/degensac/$f.c" -o "$OUT/obj_d/$f.o" &
 done
+# second flavour of the two drivers with the reference's own compile-time option __FINAL_LSQ__ (exp_ranF.h:28-29,
+# exp_ranH.c:16): the oracle of DGB200_FLAG_FINAL_LSQ
+mkdir -p "$OUT/obj_l"
+# (exp_ranH.c only: the F driver's __FINAL_LSQ__ text assigns a Score to an unsigned, exp_ranF.c:1702, and does not compile)
+gcc $CFLAGS -D__FINAL_LSQ__ -c "$SRC/degensac/exp_ranH.c" -o "$OUT/obj_l/exp_ranH.o" &
 wait
-rm -f "$OUT/libmatutls.a" "$OUT/libdegensac_support.a"
+rm -f "$OUT/libmatutls.a" "$OUT/libdegensac_support.a" "$OUT/libdegensac_support_lsq.a"
 ar rcs "$OUT/libmatutls.a" "$OUT"/obj_m/*.o
 ar rcs "$OUT/libdegensac_support.a" "$OUT"/obj_d/*.o
+cp "$OUT/obj_l/exp_ranH.o" "$OUT/obj_d/exp_ranH.o"
+ar rcs "$OUT/libdegensac_support_lsq.a" "$OUT"/obj_d/*.o
 # LAPACK (dsyev_/dgesvd_): third party, unpinned in the reference (CMakeLists.txt:6). Use the OpenBLAS 0.3.15
 # that ships inside the opencv-python-headless wheel of this image.
 SP="$(python -c 'import sysconfig; print(sysconfig.get_paths()["purelib"])')"
@@ -40,5 +47,9 @@ gcc -O2 -fPIC -shared -o "$OUT/libdegensac_ref.so" "$HERE/ref_harness.c" \
   -Wl,--wrap=time,--wrap=srand,--wrap=rand,--wrap=random \
   -Wl,--whole-archive "$OUT/libdegensac_support.a" -Wl,--no-whole-archive "$OUT/libmatutls.a" \
   "$BLAS" -Wl,--disable-new-dtags,-rpath,"$BLASDIR" -lm
-rm -rf "$OUT/obj_m" "$OUT/obj_d"
-echo "build_ref: built $OUT/libdegensac_ref.so (LAPACK: $BLAS)"
+gcc -O2 -fPIC -shared -o "$OUT/libdegensac_ref_lsq.so" "$HERE/ref_harness.c" \
+  -Wl,--wrap=time,--wrap=srand,--wrap=rand,--wrap=random \
+  -Wl,--whole-archive "$OUT/libdegensac_support_lsq.a" -Wl,--no-whole-archive "$OUT/libmatutls.a" \
+  "$BLAS" -Wl,--disable-new-dtags,-rpath,"$BLASDIR" -lm
+rm -rf "$OUT/obj_m" "$OUT/obj_d" "$OUT/obj_l"
+echo "build_ref: built $OUT/libdegensac_ref.so and libdegensac_ref_lsq.so (LAPACK: $BLAS)"

@@ -31,7 +31,8 @@ def _dp(a):
 
 
 def find_fundamental(pts1, pts2, px_th=0.5, conf=0.9999, max_iters=100000, error_type=0, sym_check=True, laf_coef=0.0,
-                     degen_check=True, seed=0):
+                     degen_check=True, seed=0, final_lsq=False):
+    lib().port_set_final_lsq(int(bool(final_lsq)))
     p1 = np.ascontiguousarray(pts1, dtype=np.float64); p2 = np.ascontiguousarray(pts2, dtype=np.float64)
     n, dim = p1.shape
     F = np.zeros(9); mask = np.zeros(n, dtype=np.uint8); stats = np.zeros(4, dtype=np.int32)
@@ -46,7 +47,8 @@ def find_fundamental(pts1, pts2, px_th=0.5, conf=0.9999, max_iters=100000, error
 
 
 def find_homography_raw(pts1, pts2, px_th=1.0, conf=0.999, max_iters=50000, error_type=0, sym_check=True, laf_coef=0.0,
-                        seed=0):
+                        seed=0, final_lsq=False):
+    lib().port_set_final_lsq(int(bool(final_lsq)))
     p1 = np.ascontiguousarray(pts1, dtype=np.float64); p2 = np.ascontiguousarray(pts2, dtype=np.float64)
     n, dim = p1.shape
     H = np.zeros(9); mask = np.zeros(n, dtype=np.uint8); stats = np.zeros(4, dtype=np.int32)

@@ -721,6 +721,9 @@ static unsigned lafcountF(int metric, const double *F, const Pts *L1, const Pts 
   return c2 < c1 ? c2 : c1;
 }
 
+static int g_final_lsq = 0;   /* the reference's compile-time option __FINAL_LSQ__ (exp_ranF.h:28-29, exp_ranH.c:16) as a run-time switch */
+void port_set_final_lsq(int on) { g_final_lsq = on; }
+
 int port_find_fundamental(const double *x1y1, const double *x2y2, int n, int dim, double px_th, double conf, int max_iters,
                           int error_type, int sym_check, double laf_coef, int degen, uint64_t seed, double *F_out,
                           unsigned char *mask, int *stats) {
@@ -852,6 +855,9 @@ int port_find_fundamental(const double *x1y1, const double *x2y2, int n, int dim
     }
   }
   { double *d = errs[3];   /* :1699-1723, including the list-position indexing of the symmetric prune (App. A#4) */
+    if (g_final_lsq) {   /* #ifdef __FINAL_LSQ__ (:1701-1705).  The reference's text `I = inlidxs(...)` assigns a Score to an
+                            unsigned and does not compile (exp_ranF.c:1702); restated with the evident `.I`. */
+      S = inlidxs(d, n, th, inliers); u2f(&P, inliers, (int)S.I, NULL, F); fres_all(fp.metric, F, &P, d); }
     for (int j = 0; j < n; ++j) mask[j] = d[j] <= th;
     if (fp.do_sym) { S = inlidxs(d, n, th, inliers); for (unsigned j = 0; j < S.I; ++j) if (fres(1, F, &P, inliers[j]) > fp.sym_th) mask[j] = 0; } }
   double asum = 0; for (int i = 0; i < 9; ++i) { F_out[i] = F[i]; asum += fabs(F[i]); }
@@ -985,6 +991,7 @@ int port_find_homography(const double *x1y1, const double *x2y2, int n, int dim,
   if (st.k != (uint32_t)no_sam) { st.k = (uint32_t)no_sam; st.j = 5; }
   if (iter_cnt == 0) { ++iter_cnt; memcpy(h, H, 72); lo_step_H(&P, &hp, errs, inliers, inliersS, h, H, &maxS, &iterID, &ht, &st); }   /* :759-862 */
   { double *d = errs[3];
+    if (g_final_lsq) { Sc Sl = inlidxs(d, n, th, inliers); u2h(&P, inliers, (int)Sl.I, H); hres_all(hp.metric, H, &P, d); }   /* #ifdef __FINAL_LSQ__, exp_ranH.c:866-870 */
     for (int j = 0; j < n; ++j) mask[j] = d[j] <= th;
     if (hp.do_sym) { Sc Sc2 = inlidxs(d, n, th, inliersS); HS s; hsym(H, &s); for (unsigned j = 0; j < Sc2.I; ++j) if (hgate(&s, &P, inliersS[j]) > hp.sym_th) mask[inliersS[j]] = 0; }
     if (hp.do_laf) {   /* final LAF prune, :889-907 (HDSidx1 on both helper correspondences) */

@@ -12,7 +12,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libdegensac_ref.so")
+_SO_LSQ = os.path.join(_HERE, "_ref", "libdegensac_ref_lsq.so")   # the same sources compiled with -D__FINAL_LSQ__
 _lib = None
+_lib_lsq = None
 
 RNG_GLIBC = 0   # reference's own rand()/random(), seeded from the (settable) time
 RNG_PHILOX = 1  # replay of the engine's counter-based stream
@@ -22,11 +24,25 @@ def available():
     return os.path.exists(_SO)
 
 
-def lib():
-    global _lib
+def available_final_lsq():
+    return os.path.exists(_SO_LSQ)
+
+
+def lib(final_lsq=False):
+    global _lib, _lib_lsq
+    if final_lsq:
+        if _lib_lsq is None:
+            os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+            _lib_lsq = _declare(ctypes.CDLL(_SO_LSQ))
+        return _lib_lsq
     if _lib is None:
         os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-        _lib = ctypes.CDLL(_SO)
+        _lib = _declare(ctypes.CDLL(_SO))
+    return _lib
+
+
+def _declare(_lib):
+    if True:   # (same exports in both flavours)
         dp = ctypes.POINTER(ctypes.c_double)
         _lib.ref_find_fundamental.argtypes = [dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
@@ -50,15 +66,19 @@ def _dptr(a):
 
 
 def find_fundamental(pts1, pts2, px_th=0.5, conf=0.9999, max_iters=100000, error_type=0, sym_check=True,
-                     laf_coef=0.0, degen_check=True, seed=0, rng=RNG_PHILOX):
-    """Reference exp_ransacFcustomLAF behind the binding-layer conventions. Returns (F 3x3, mask bool[N], stats[4])."""
+                     laf_coef=0.0, degen_check=True, seed=0, rng=RNG_PHILOX, final_lsq=False):
+    """Reference exp_ransacFcustomLAF behind the binding-layer conventions. Returns (F 3x3, mask bool[N], stats[4]).
+    (final_lsq is accepted for symmetry but the reference's F text under __FINAL_LSQ__ does not compile,
+    exp_ranF.c:1702; the F polish is pinned by oracle/port instead.)"""
+    if final_lsq:
+        raise ValueError("the reference has no compilable F driver with __FINAL_LSQ__")
     p1 = np.ascontiguousarray(pts1, dtype=np.float64)
     p2 = np.ascontiguousarray(pts2, dtype=np.float64)
     n, dim = p1.shape
     F = np.zeros(9, dtype=np.float64)
     mask = np.zeros(n, dtype=np.uint8)
     stats = np.zeros(4, dtype=np.int32)
-    rc = lib().ref_find_fundamental(_dptr(p1), _dptr(p2), n, dim, px_th, conf, int(max_iters), int(error_type),
+    rc = lib(final_lsq).ref_find_fundamental(_dptr(p1), _dptr(p2), n, dim, px_th, conf, int(max_iters), int(error_type),
                                     int(bool(sym_check)), float(max(0.0, laf_coef)), int(bool(degen_check)), int(rng),
                                     ctypes.c_uint64(int(seed)), _dptr(F),
                                     mask.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
@@ -69,7 +89,7 @@ def find_fundamental(pts1, pts2, px_th=0.5, conf=0.9999, max_iters=100000, error
 
 
 def find_homography_raw(pts1, pts2, px_th=1.0, conf=0.999, max_iters=50000, error_type=0, sym_check=True,
-                        laf_coef=0.0, seed=0, rng=RNG_PHILOX):
+                        laf_coef=0.0, seed=0, rng=RNG_PHILOX, final_lsq=False):
     """Reference exp_ransacHcustomLAF; returns the RAW core output (9 doubles, column-major, maps image2->image1)."""
     p1 = np.ascontiguousarray(pts1, dtype=np.float64)
     p2 = np.ascontiguousarray(pts2, dtype=np.float64)
@@ -77,7 +97,7 @@ def find_homography_raw(pts1, pts2, px_th=1.0, conf=0.999, max_iters=50000, erro
     H = np.zeros(9, dtype=np.float64)
     mask = np.zeros(n, dtype=np.uint8)
     stats = np.zeros(4, dtype=np.int32)
-    rc = lib().ref_find_homography(_dptr(p1), _dptr(p2), n, dim, px_th, conf, int(max_iters), int(error_type),
+    rc = lib(final_lsq).ref_find_homography(_dptr(p1), _dptr(p2), n, dim, px_th, conf, int(max_iters), int(error_type),
                                    int(bool(sym_check)), float(max(0.0, laf_coef)), int(rng),
                                    ctypes.c_uint64(int(seed)), _dptr(H),
                                    mask.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),

@@ -11,6 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBPATH = os.path.join(_HERE, "libdegensac_b200.so")
 _lib = None
+FLAG_FINAL_LSQ = 1   # DGB200_FLAG_FINAL_LSQ
 
 
 class EngineUnavailable(RuntimeError):
@@ -35,10 +36,21 @@ def lib():
         vp = ctypes.c_void_p
         L.dgb200_find_fundamental_batch_dev.argtypes = [vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, ci, vp, vp, vp, vp, vp]
         L.dgb200_find_homography_batch_dev.argtypes = [vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, vp, vp, vp, vp, vp]
+        cu = ctypes.c_uint
+        L.dgb200_find_fundamental_batch_ex.argtypes = [dp, dp, ci, ci, ci, cd, cd, ci, ci, ci, cd, ci, u64, dp, u8, i32, cu]
+        L.dgb200_find_homography_batch_ex.argtypes = [dp, dp, ci, ci, ci, cd, cd, ci, ci, ci, cd, u64, dp, u8, i32, cu]
+        L.dgb200_find_fundamental_batch_dev_ex.argtypes = [vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, ci, vp, vp, vp, vp, vp, cu]
+        L.dgb200_find_homography_batch_dev_ex.argtypes = [vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, vp, vp, vp, vp, vp, cu]
         L.dgb200_find_fundamental_ragged.argtypes = [dp, dp, i32, ci, ci, cd, cd, ci, ci, ci, cd, ci, u64, dp, u8, i32]
         L.dgb200_find_homography_ragged.argtypes = [dp, dp, i32, ci, ci, cd, cd, ci, ci, ci, cd, u64, dp, u8, i32]
         L.dgb200_find_fundamental_ragged_dev.argtypes = [vp, vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, ci, vp, vp, vp, vp, vp]
         L.dgb200_find_homography_ragged_dev.argtypes = [vp, vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, vp, vp, vp, vp, vp]
+        L.dgb200_match_workspace_bytes.restype = ctypes.c_size_t
+        L.dgb200_match_workspace_bytes.argtypes = [ci, ci]
+        L.dgb200_match_descriptors_dev.argtypes = [vp, ci, vp, ci, ci, ctypes.c_float, ci, vp, vp, ci, vp, vp, vp, vp, ci, ci, vp, vp, vp]
+        L.dgb200_pose_from_fundamental_batch_dev.argtypes = [vp, vp, vp, ci, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp]
+        L.dgb200_nullspace_qr7x9_batch_dev.argtypes = [vp, vp, vp, ci, vp]
+        L.dgb200_frontend_last_error.restype = ctypes.c_char_p
         L.dgb200_last_error.restype = ctypes.c_char_p
         L.dgb200_kernel_launches.restype = ctypes.c_longlong
         L.dgb200_last_kernel_ms.restype = ctypes.c_double
@@ -74,35 +86,37 @@ def _seeds(seeds, P):
     return s
 
 
-def fundamental_batch(pts1, pts2, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check, seeds):
+def fundamental_batch(pts1, pts2, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check, seeds, flags=0):
     p1, p2 = _prep(pts1, pts2)
     P, N, dim = p1.shape
     F = np.zeros((P, 3, 3), dtype=np.float64)
     mask = np.zeros((P, N), dtype=np.uint8)
     stats = np.zeros((P, 4), dtype=np.int32)
     s = _seeds(seeds, P)
-    rc = lib().dgb200_find_fundamental_batch(_p(p1, ctypes.c_double), _p(p2, ctypes.c_double), P, N, dim,
-                                             float(px_th), float(conf), int(max_iters), int(error_type),
-                                             int(bool(sym_check)), float(laf_coef), int(bool(degen_check)),
-                                             _p(s, ctypes.c_uint64) if s is not None else None,
-                                             _p(F, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32))
+    rc = lib().dgb200_find_fundamental_batch_ex(_p(p1, ctypes.c_double), _p(p2, ctypes.c_double), P, N, dim,
+                                                float(px_th), float(conf), int(max_iters), int(error_type),
+                                                int(bool(sym_check)), float(laf_coef), int(bool(degen_check)),
+                                                _p(s, ctypes.c_uint64) if s is not None else None,
+                                                _p(F, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32),
+                                                int(flags))
     if rc != 0:
         _raise(rc)
     return F, mask.view(np.bool_), stats
 
 
-def homography_batch(pts1, pts2, px_th, conf, max_iters, error_type, sym_check, laf_coef, seeds):
+def homography_batch(pts1, pts2, px_th, conf, max_iters, error_type, sym_check, laf_coef, seeds, flags=0):
     p1, p2 = _prep(pts1, pts2)
     P, N, dim = p1.shape
     H = np.zeros((P, 3, 3), dtype=np.float64)
     mask = np.zeros((P, N), dtype=np.uint8)
     stats = np.zeros((P, 4), dtype=np.int32)
     s = _seeds(seeds, P)
-    rc = lib().dgb200_find_homography_batch(_p(p1, ctypes.c_double), _p(p2, ctypes.c_double), P, N, dim,
-                                            float(px_th), float(conf), int(max_iters), int(error_type),
-                                            int(bool(sym_check)), float(laf_coef),
-                                            _p(s, ctypes.c_uint64) if s is not None else None,
-                                            _p(H, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32))
+    rc = lib().dgb200_find_homography_batch_ex(_p(p1, ctypes.c_double), _p(p2, ctypes.c_double), P, N, dim,
+                                               float(px_th), float(conf), int(max_iters), int(error_type),
+                                               int(bool(sym_check)), float(laf_coef),
+                                               _p(s, ctypes.c_uint64) if s is not None else None,
+                                               _p(H, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32),
+                                               int(flags))
     if rc != 0:
         _raise(rc)
     return H, mask.view(np.bool_), stats
@@ -161,20 +175,21 @@ def homography_ragged(list1, list2, px_th, conf, max_iters, error_type, sym_chec
 
 
 def fundamental_batch_dev(d_p1, d_p2, P, N, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, degen_check,
-                          d_seeds, d_F, d_mask, d_stats, stream=0):
+                          d_seeds, d_F, d_mask, d_stats, stream=0, flags=0):
     """Device-pointer flavour: all d_* are integer device addresses (e.g. torch.Tensor.data_ptr())."""
-    rc = lib().dgb200_find_fundamental_batch_dev(d_p1, d_p2, P, N, dim, float(px_th), float(conf), int(max_iters),
-                                                 int(error_type), int(bool(sym_check)), float(laf_coef),
-                                                 int(bool(degen_check)), d_seeds, d_F, d_mask, d_stats, stream)
+    rc = lib().dgb200_find_fundamental_batch_dev_ex(d_p1, d_p2, P, N, dim, float(px_th), float(conf), int(max_iters),
+                                                    int(error_type), int(bool(sym_check)), float(laf_coef),
+                                                    int(bool(degen_check)), d_seeds, d_F, d_mask, d_stats, stream,
+                                                    int(flags))
     if rc != 0:
         _raise(rc)
 
 
 def homography_batch_dev(d_p1, d_p2, P, N, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, d_seeds,
-                         d_H, d_mask, d_stats, stream=0):
-    rc = lib().dgb200_find_homography_batch_dev(d_p1, d_p2, P, N, dim, float(px_th), float(conf), int(max_iters),
-                                                int(error_type), int(bool(sym_check)), float(laf_coef), d_seeds, d_H,
-                                                d_mask, d_stats, stream)
+                         d_H, d_mask, d_stats, stream=0, flags=0):
+    rc = lib().dgb200_find_homography_batch_dev_ex(d_p1, d_p2, P, N, dim, float(px_th), float(conf), int(max_iters),
+                                                   int(error_type), int(bool(sym_check)), float(laf_coef), d_seeds, d_H,
+                                                   d_mask, d_stats, stream, int(flags))
     if rc != 0:
         _raise(rc)
 

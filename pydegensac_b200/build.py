@@ -31,10 +31,11 @@ def _csrc_files():
 
 def build_cuda(force=False, verbose=False):
     src = os.path.join(CSRC, "degensac_b200.cu")
+    src2 = os.path.join(CSRC, "frontend.cu")      # matcher / pose / QR null space (the steps either side of the path)
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest(_csrc_files()):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, src]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, src, src2]
     subprocess.check_call(cmd)
     return LIB
 

@@ -76,6 +76,7 @@ struct BatchArgs {
   int n_pairs, n, dim;  // n: correspondences per pair (ragged: the largest, which sizes the slabs)
   double px_th, conf, laf_coef;
   int max_iters, metric, sym_check, degen;
+  unsigned flags;       // DGB200_FLAG_*
   const unsigned long long* seeds;
   double* model_out;
   unsigned char* mask_out;
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
       P.conf = a.conf; P.laf_coef = a.laf_coef; P.max_iters = a.max_iters; P.metric = a.metric; P.degen = a.degen;
       P.do_laf = use_laf ? 1 : 0; P.th_laf = a.laf_coef * P.th;
       P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = a.chunk;
+      P.final_lsq = (a.flags & DGB200_FLAG_FINAL_LSQ) ? 1 : 0;
       dg::ransac_F_pair(c, P, W, model, mask, s_stats);
     } else {
       dg::HParams P;
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
       P.conf = a.conf; P.laf_coef = a.laf_coef; P.max_iters = a.max_iters; P.metric = a.metric;
       P.do_laf = use_laf ? 1 : 0; P.th_laf = a.laf_coef * P.th;
       P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = a.chunk;
+      P.final_lsq = (a.flags & DGB200_FLAG_FINAL_LSQ) ? 1 : 0;
       dg::ransac_H_pair(c, P, W, model, mask, s_stats);
     }
     __syncthreads();
@@ -331,6 +334,7 @@ struct Job {
   int n_pairs, n, dim;
   double px_th, conf, laf_coef;
   int max_iters, metric, sym_check, degen;
+  unsigned flags;
   const unsigned long long* d_seeds;
   double* d_model; unsigned char* d_mask; int* d_stats;
 };
@@ -341,7 +345,7 @@ int launch(const Job& j, cudaStream_t st, const int* d_ready = nullptr, int* d_s
   a.ready = d_ready; a.status = d_status; a.wait_cycles = wait_cycles;
   a.x1y1 = j.d1; a.x2y2 = j.d2; a.offsets = j.d_offsets; a.n_pairs = j.n_pairs; a.n = j.n; a.dim = j.dim;
   a.px_th = j.px_th; a.conf = j.conf; a.laf_coef = j.laf_coef; a.max_iters = j.max_iters; a.metric = j.metric;
-  a.sym_check = j.sym_check; a.degen = j.degen; a.seeds = j.d_seeds;
+  a.sym_check = j.sym_check; a.degen = j.degen; a.flags = j.flags; a.seeds = j.d_seeds;
   a.model_out = j.d_model; a.mask_out = j.d_mask; a.stats_out = j.d_stats;
   a.chunk = kChunk;
   const int n = j.n;
@@ -423,7 +427,7 @@ int check_offsets(int kind, const int32_t* offsets, int n_pairs, int* n_max, lon
 template <int KIND>
 int run_host(const double* x1y1, const double* x2y2, const int32_t* offsets, int n_pairs, int n, int dim, double px_th,
              double conf, int max_iters, int metric, int sym_check, double laf_coef, int degen, const uint64_t* seeds,
-             double* model_out, uint8_t* mask_out, int32_t* stats_out) {
+             double* model_out, uint8_t* mask_out, int32_t* stats_out, unsigned flags = 0) {
   std::lock_guard<std::mutex> lk(g_mu);
   long long rows = (long long)n_pairs * n;
   if (offsets) {
@@ -459,7 +463,7 @@ int run_host(const double* x1y1, const double* x2y2, const int32_t* offsets, int
   Job j;
   j.d1 = d1; j.d2 = d2; j.d_offsets = offsets ? doff : nullptr; j.n_pairs = n_pairs; j.n = n; j.dim = dim;
   j.px_th = px_th; j.conf = conf; j.laf_coef = laf_coef; j.max_iters = max_iters; j.metric = metric;
-  j.sym_check = sym_check; j.degen = degen; j.d_seeds = seeds ? dseed : nullptr;
+  j.sym_check = sym_check; j.degen = degen; j.flags = flags; j.d_seeds = seeds ? dseed : nullptr;
   j.d_model = dmodel; j.d_mask = dmask; j.d_stats = dstats;
   // Input feed overlapped with the kernel: the batch is copied in chunks on a copy stream; after every chunk the
   // device-side `ready` count is bumped (a 4-byte copy from pinned memory, ordered behind the chunk) and the
@@ -545,7 +549,7 @@ int run_host(const double* x1y1, const double* x2y2, const int32_t* offsets, int
 template <int KIND>
 int run_dev(const double* d1, const double* d2, const int32_t* d_offsets, int n_pairs, int n, int dim, double px_th,
             double conf, int max_iters, int metric, int sym_check, double laf_coef, int degen, const uint64_t* d_seeds,
-            double* d_model, uint8_t* d_mask, int32_t* d_stats, void* stream) {
+            double* d_model, uint8_t* d_mask, int32_t* d_stats, void* stream, unsigned flags = 0) {
   std::lock_guard<std::mutex> lk(g_mu);
   int rc = check_args(KIND, d1, d2, n_pairs, n, dim, metric, laf_coef, d_model, d_mask);
   if (rc) return rc;
@@ -554,7 +558,7 @@ int run_dev(const double* d1, const double* d2, const int32_t* d_offsets, int n_
   Job j;
   j.d1 = d1; j.d2 = d2; j.d_offsets = d_offsets; j.n_pairs = n_pairs; j.n = n; j.dim = dim;
   j.px_th = px_th; j.conf = conf; j.laf_coef = laf_coef; j.max_iters = max_iters; j.metric = metric;
-  j.sym_check = sym_check; j.degen = degen; j.d_seeds = (const unsigned long long*)d_seeds;
+  j.sym_check = sym_check; j.degen = degen; j.flags = flags; j.d_seeds = (const unsigned long long*)d_seeds;
   j.d_model = d_model; j.d_mask = d_mask; j.d_stats = d_stats;
   return launch<KIND>(j, (cudaStream_t)stream);
 }
@@ -575,6 +579,34 @@ int dgb200_find_homography_batch(const double* x1y1, const double* x2y2, int n_p
                                  const uint64_t* seeds, double* H_out, uint8_t* mask_out, int32_t* stats_out) {
   return run_host<1>(x1y1, x2y2, nullptr, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0,
                      seeds, H_out, mask_out, stats_out);
+}
+int dgb200_find_fundamental_batch_ex(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim, double px_th,
+                                     double conf, int max_iters, int error_type, int sym_check, double laf_coef,
+                                     int degen_check, const uint64_t* seeds, double* F_out, uint8_t* mask_out,
+                                     int32_t* stats_out, unsigned flags) {
+  return run_host<0>(x1y1, x2y2, nullptr, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef,
+                     degen_check, seeds, F_out, mask_out, stats_out, flags);
+}
+int dgb200_find_homography_batch_ex(const double* x1y1, const double* x2y2, int n_pairs, int n, int dim, double px_th,
+                                    double conf, int max_iters, int error_type, int sym_check, double laf_coef,
+                                    const uint64_t* seeds, double* H_out, uint8_t* mask_out, int32_t* stats_out,
+                                    unsigned flags) {
+  return run_host<1>(x1y1, x2y2, nullptr, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0,
+                     seeds, H_out, mask_out, stats_out, flags);
+}
+int dgb200_find_fundamental_batch_dev_ex(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
+                                         double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                         double laf_coef, int degen_check, const uint64_t* d_seeds, double* d_F_out,
+                                         uint8_t* d_mask_out, int32_t* d_stats_out, void* stream, unsigned flags) {
+  return run_dev<0>(d_x1y1, d_x2y2, nullptr, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef,
+                    degen_check, d_seeds, d_F_out, d_mask_out, d_stats_out, stream, flags);
+}
+int dgb200_find_homography_batch_dev_ex(const double* d_x1y1, const double* d_x2y2, int n_pairs, int n, int dim,
+                                        double px_th, double conf, int max_iters, int error_type, int sym_check,
+                                        double laf_coef, const uint64_t* d_seeds, double* d_H_out, uint8_t* d_mask_out,
+                                        int32_t* d_stats_out, void* stream, unsigned flags) {
+  return run_dev<1>(d_x1y1, d_x2y2, nullptr, n_pairs, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0,
+                    d_seeds, d_H_out, d_mask_out, d_stats_out, stream, flags);
 }
 int dgb200_find_fundamental_ragged(const double* x1y1, const double* x2y2, const int32_t* offsets, int n_pairs, int dim,
                                    double px_th, double conf, int max_iters, int error_type, int sym_check,

@@ -481,7 +481,12 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
 // Final inlier mask (exp_ranF.c:1699-1723) incl. the reference's indexing quirk in the symmetric prune
 // (it clears mask[j] for the j-th LIST POSITION instead of mask[inliers[j]]).
 DG_ENGN void final_mask_F(const Ctx& c, const FParams& P, Workspace& W, FState& st, unsigned char* mask) {
-  const double* d = W.err[st.e[3]];
+  double* d = W.err[st.e[3]];
+  if (P.final_lsq) {   // exp_ranF.c:1701-1705: LSQ on all inliers of the best model, residuals (and the mask) from it
+    const Score Sl = blk_inlidxs(c, d, P.th, W.inliers);
+    blk_fit_F(c, W.inliers, (int)Sl.I, nullptr, st.F);
+    blk_resid_F(c, P.metric, st.F, d);
+  }
   #pragma unroll 1
   for (int j = c.tid; j < c.N; j += c.nt) mask[j] = (d[j] <= P.th) ? 1 : 0;
   DG_SYNC();

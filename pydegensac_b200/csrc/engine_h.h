@@ -25,6 +25,7 @@ struct HParams {
   int max_iters, metric, do_sym;
   uint64_t seed;
   int chunk;
+  int final_lsq;    // __FINAL_LSQ__ (exp_ranH.c:16, 866-870)
 };
 
 DG_ENGN void blk_resid_H(const Ctx& c, int metric, const double* h, double* out) {
@@ -385,7 +386,12 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
     run_lo_H(c, P, W, st, h);
   }
 
-  const double* d = W.err[st.e[3]];
+  double* d = W.err[st.e[3]];
+  if (P.final_lsq) {   // exp_ranH.c:866-870: LSQ on all inliers of the best model, residuals (and the mask) from it
+    const Score Sl = blk_inlidxs(c, d, P.th, W.inliers);
+    blk_fit_H(c, W.inliers, (int)Sl.I, st.H);
+    blk_resid_H(c, P.metric, st.H, d);
+  }
   #pragma unroll 1
   for (int j = c.tid; j < c.N; j += c.nt) mask_out[j] = (d[j] <= P.th) ? 1 : 0;
   DG_SYNC();

@@ -45,6 +45,7 @@ struct FParams {
   int max_iters, metric, degen, do_sym;
   uint64_t seed;
   int chunk;
+  int final_lsq;    // the reference's compile-time __FINAL_LSQ__ (exp_ranF.h:28-29): one more LSQ on the inliers of the best model
 };
 
 // ------------------------------------------------------------------ block-wide passes over the pair

@@ -489,6 +489,115 @@ DG_HDN void left_null_9xk(double* Z, int len, double* q) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Null space of the 7 x 9 system of a 7-point sample by column-pivoted Householder QR and back substitution: the
+// reference's alternative minimal solver nullspace_qr7x9 (Ftools.c:594-668, selected at compile time by USE_QR,
+// exp_ranF.c:1346-1349), which calls LAPACK dgeqp3_.  dgeqp3 on a 7 x 9 matrix runs its unblocked kernel dlaqp2
+// (pivot = first column of largest partial norm, dlarfg reflectors, norm downdating with the sqrt(eps) safeguard);
+// that kernel is restated here so that the pivot order -- which fixes WHICH two coordinates of the basis vectors are
+// the unit/zero pair -- follows LAPACK's.  A: 7 x 9 row-major; N: two null vectors of 9 (x_1 has 1 at the last pivoted
+// column, x_2 at the one before).  Returns 0, or -1 on a zero diagonal of R (as the reference).
+// ---------------------------------------------------------------------------------------------
+DG_HDN int nullspace_qr7x9(const double* A, double* N) {
+  const int rows = 7, cols = 9;
+  double T[63], vn1[9], vn2[9];
+  int p[9];
+  #pragma unroll 1
+  for (int i = 0; i < rows; ++i)
+    #pragma unroll 1
+    for (int j = 0; j < cols; ++j) T[i + rows * j] = A[cols * i + j];
+  #pragma unroll 1
+  for (int j = 0; j < cols; ++j) {
+    double ss = 0.0;
+    #pragma unroll 1
+    for (int i = 0; i < rows; ++i) ss += T[i + rows * j] * T[i + rows * j];
+    vn1[j] = sqrt(ss); vn2[j] = vn1[j]; p[j] = j;
+  }
+  const double tol3z = 1.4901161193847656e-08;   // sqrt(dlamch('Epsilon')) = sqrt(2^-53)... LAPACK: sqrt(eps), eps = 2^-53
+  #pragma unroll 1
+  for (int i = 0; i < rows; ++i) {
+    int pvt = i;
+    #pragma unroll 1
+    for (int j = i + 1; j < cols; ++j) if (vn1[j] > vn1[pvt]) pvt = j;
+    if (pvt != i) {
+      #pragma unroll 1
+      for (int r = 0; r < rows; ++r) { const double t = T[r + rows * pvt]; T[r + rows * pvt] = T[r + rows * i]; T[r + rows * i] = t; }
+      const int tp = p[pvt]; p[pvt] = p[i]; p[i] = tp;
+      vn1[pvt] = vn1[i]; vn2[pvt] = vn2[i];
+    }
+    // reflector H(i) (dlarfg)
+    double tau = 0.0;
+    if (i < rows - 1) {
+      double xn = 0.0;
+      #pragma unroll 1
+      for (int r = i + 1; r < rows; ++r) xn += T[r + rows * i] * T[r + rows * i];
+      xn = sqrt(xn);
+      if (xn != 0.0) {
+        const double alpha = T[i + rows * i];
+        double beta = sqrt(alpha * alpha + xn * xn);
+        if (alpha >= 0.0) beta = -beta;
+        tau = (beta - alpha) / beta;
+        const double sc = 1.0 / (alpha - beta);
+        #pragma unroll 1
+        for (int r = i + 1; r < rows; ++r) T[r + rows * i] *= sc;
+        T[i + rows * i] = beta;
+      }
+    }
+    // apply H(i)^T to the trailing columns (dlarf, side = left), v = (1, T[i+1.., i])
+    if (tau != 0.0) {
+      #pragma unroll 1
+      for (int j = i + 1; j < cols; ++j) {
+        double w = T[i + rows * j];
+        #pragma unroll 1
+        for (int r = i + 1; r < rows; ++r) w += T[r + rows * i] * T[r + rows * j];
+        w *= tau;
+        T[i + rows * j] -= w;
+        #pragma unroll 1
+        for (int r = i + 1; r < rows; ++r) T[r + rows * j] -= w * T[r + rows * i];
+      }
+    }
+    // partial column norms (dlaqp2)
+    #pragma unroll 1
+    for (int j = i + 1; j < cols; ++j) {
+      if (vn1[j] != 0.0) {
+        double temp = fabs(T[i + rows * j]) / vn1[j];
+        temp = 1.0 - temp * temp;
+        if (temp < 0.0) temp = 0.0;
+        const double q = vn1[j] / vn2[j];
+        const double temp2 = temp * (q * q);
+        if (temp2 <= tol3z) {
+          if (i < rows - 1) {
+            double ss = 0.0;
+            #pragma unroll 1
+            for (int r = i + 1; r < rows; ++r) ss += T[r + rows * j] * T[r + rows * j];
+            vn1[j] = sqrt(ss); vn2[j] = vn1[j];
+          } else { vn1[j] = 0.0; vn2[j] = 0.0; }
+        } else {
+          vn1[j] *= sqrt(temp);
+        }
+      }
+    }
+  }
+  // back substitution (Ftools.c:646-666)
+  double* sol = N;
+  #pragma unroll 1
+  for (int k = 1; k <= cols - rows; ++k) {
+    #pragma unroll 1
+    for (int c = rows; c < cols; ++c) sol[p[c]] = 0.0;
+    sol[p[cols - k]] = 1.0;
+    #pragma unroll 1
+    for (int r = rows - 1; r >= 0; --r) {
+      if (T[r * rows + r] == 0.0) return -1;
+      double a = 0.0;
+      #pragma unroll 1
+      for (int c = r + 1; c < cols; ++c) a += T[c * rows + r] * sol[p[c]];
+      sol[p[r]] = -a / T[r * rows + r];
+    }
+    sol += cols;
+  }
+  return 0;
+}
+
 // 3x3 inverse in place (row-major) by Gauss-Jordan with partial pivoting.  Returns nonzero when a
 // pivot falls below 1e-15 x the largest pivot seen so far (the singularity rule of CCMATH minv,
 // matutls/minv.c:11,27), in which case the matrix content is unspecified.

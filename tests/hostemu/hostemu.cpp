@@ -29,6 +29,8 @@ struct Emu {
   double* soa;
 };
 
+static int g_final_lsq = 0;
+extern "C" void emu_set_final_lsq(int on) { g_final_lsq = on; }
 static int g_poison = 0;
 extern "C" void emu_set_poison(int v) { g_poison = v; }
 static void emu_setup(Emu& E, const double* x1y1, const double* x2y2, int n, int dim, int chunk) {
@@ -69,7 +71,7 @@ extern "C" int emu_find_fundamental(const double* x1y1, const double* x2y2, int 
   f_thresholds(px_th, sym_check, &P.th, &P.sym_th);
   P.conf = conf; P.laf_coef = laf_coef; P.max_iters = max_iters; P.metric = error_type; P.degen = degen;
   P.do_laf = laf_coef > 0 ? 1 : 0; P.th_laf = laf_coef * P.th;
-  P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk;
+  P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk; P.final_lsq = g_final_lsq;
   if (g_use_filter32) { blk_prepare_tile32(E.c, E.tile, &E.t32); E.c.t32 = &E.t32; }
   ransac_F_pair(E.c, P, E.W, F, mask, stats);
   free(E.slab); free(E.tile);
@@ -87,7 +89,7 @@ extern "C" int emu_find_homography(const double* x1y1, const double* x2y2, int n
   if (h_thresholds(error_type, px_th, sym_check, &P.th, &P.sym_th)) return -2;
   P.conf = conf; P.laf_coef = laf_coef; P.max_iters = max_iters; P.metric = error_type;
   P.do_laf = laf_coef > 0 ? 1 : 0; P.th_laf = laf_coef * P.th;
-  P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk;
+  P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk; P.final_lsq = g_final_lsq;
   ransac_H_pair(E.c, P, E.W, H, mask, stats);
   free(E.slab); free(E.tile);
   return 0;
@@ -101,6 +103,7 @@ extern "C" double emu_f_resid(int metric, const double* F, double x1, double y1,
 extern "C" double emu_h_resid(int metric, const double* H, double x1, double y1, double x2, double y2) {
   HSym s; h_sym_prepare(H, &s); return h_resid_metric(metric, H, s, x1, y1, x2, y2);
 }
+extern "C" int emu_nullspace_qr7x9(const double* A, double* N) { return nullspace_qr7x9(A, N); }
 extern "C" uint32_t emu_hash(const int* idx, int n) { return superfasthash_i32(idx, n); }
 extern "C" int emu_nsamples(int a, int b, int c, double d) { return nsamples(a, b, c, d); }
 extern "C" void emu_min_eigvec9(double* C, double* v) { min_eigvec9(C, v); }
