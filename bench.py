@@ -334,6 +334,8 @@ def run_gpu_arm(args):
         times.append(e0.elapsed_time(e1))
     barrier()
     launches = _cabi.kernel_launches() - launches0
+    sampler.stop_flag = True        # (its nvidia-smi forks would perturb the host-side e2e leg below)
+    sampler.join(2.0)
     total_ms = float(sum(times))
     tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -376,7 +378,6 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * P * args.steps / float(te.item())
-    sampler.stop_flag = True
 
     # the gathered records are what a caller gets: rank 0 recomputes a sample of every rank's block and compares
     gather_check = None

@@ -27,7 +27,7 @@ if __name__ == "__main__":
     from pydegensac_b200 import _cabi
     b1, b2 = batch_F(P, 2000, 0.3, seed0=0, plane_frac=plane)
     F, m, s = _cabi.fundamental_batch(b1, b2, 1.0, 0.9999, 10000, 0, True, 0.0, True, np.arange(P, dtype=np.uint64))
-    nproc = 16
+    nproc = min(16, os.cpu_count() or 1)
     chunks = [(i * P // nproc, (i + 1) * P // nproc) for i in range(nproc)]
     with get_context("fork").Pool(nproc) as pool:
         res = sum(pool.map(work, chunks), [])
