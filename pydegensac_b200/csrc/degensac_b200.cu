@@ -102,13 +102,14 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
   const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128);
   dg::Workspace W;
   double* soa_global;
-  dg::workspace_carve(a.workspace + (size_t)blockIdx.x * a.ws_stride, a.n, a.chunk, &W, &soa_global);
+  const bool use_laf = (a.laf_coef > 0) && (a.dim == 6);
+  dg::workspace_carve(a.workspace + (size_t)blockIdx.x * a.ws_stride, a.n, a.chunk, use_laf, &W, &soa_global);
   const size_t row = dg::align_up(sizeof(double) * (size_t)a.n, 128) / sizeof(double);
   double* soa = a.pts_in_smem ? reinterpret_cast<double*>(smem_raw + sc_bytes) : soa_global;
   const size_t soa_smem_bytes = a.pts_in_smem ? dg::align_up(sizeof(double) * (size_t)a.n, 128) * 4 : 0;
   dg::Pt32* tile32 = a.tile32_in_smem
                          ? reinterpret_cast<dg::Pt32*>(smem_raw + sc_bytes + soa_smem_bytes)
-                         : reinterpret_cast<dg::Pt32*>(dg::workspace_tile32(a.workspace + (size_t)blockIdx.x * a.ws_stride, a.n, a.chunk));
+                         : reinterpret_cast<dg::Pt32*>(dg::workspace_tile32(a.workspace + (size_t)blockIdx.x * a.ws_stride, a.n, a.chunk, use_laf));
   dg::Tile32 t32;
 
   dg::Ctx c;
@@ -117,7 +118,6 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
   c.x1 = soa; c.y1 = soa + row; c.x2 = soa + 2 * row; c.y2 = soa + 3 * row;
   c.sc = sc;
   c.t32 = nullptr;
-  const bool use_laf = (a.laf_coef > 0) && (a.dim == 6);
   for (int i = 0; i < 8; ++i) c.laf[i] = use_laf ? W.laf[i] : nullptr;
 
   for (;;) {
@@ -192,6 +192,11 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
       P.final_lsq = (a.flags & DGB200_FLAG_FINAL_LSQ) ? 1 : 0;
       dg::ransac_F_pair(c, P, W, model, mask, s_stats);
     } else {
+      c.t32 = nullptr;
+      if (a.filter32 && a.metric == dg::H_SAMPSON) {   // FP32 upper-bound filter of the H wave (Sampson metric)
+        dg::blk_prepare_tile32(c, tile32, &t32);
+        c.t32 = &t32;
+      }
       dg::HParams P;
       dg::h_thresholds(a.metric, a.px_th, a.sym_check, &P.th, &P.sym_th);
       P.conf = a.conf; P.laf_coef = a.laf_coef; P.max_iters = a.max_iters; P.metric = a.metric;
@@ -351,7 +356,7 @@ int launch(const Job& j, cudaStream_t st, const int* d_ready = nullptr, int* d_s
   const int n = j.n;
   const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128);
   const size_t tile = dg::align_up(sizeof(double) * (size_t)n, 128) * 4;       // FP64 SoA of the pair
-  const size_t tile32 = (KIND == 0 && 16 * (size_t)n <= 65536) ? dg::align_up(16 * (size_t)n, 128) : 0;   // FP32 filter tile
+  const size_t tile32 = (16 * ((size_t)n + 1) <= 98304) ? dg::align_up(16 * ((size_t)n + 1), 128) : 0;   // FP32 filter tile (pair-interleaved: N+1 slots)
   const int kThreads = cfg_threads();
   auto kern = ransac_pairs_kernel<KIND>;
   // Shared-memory plan: block scratch always; the FP32 filter tile when it fits.  The FP64 correspondences stay in
@@ -360,9 +365,15 @@ int launch(const Job& j, cudaStream_t st, const int* d_ready = nullptr, int* d_s
   size_t smem = sc_bytes;
   a.pts_in_smem = 0;
   a.tile32_in_smem = 0;
-  a.filter32 = (KIND == 0) ? (env_int("DGB200_FILTER32", 1) != 0) : 0;   // parity switch, read at every launch
+  a.filter32 = (env_int("DGB200_FILTER32", 1) != 0 && (KIND == 0 || j.metric == dg::H_SAMPSON)) ? 1 : 0;   // parity switch, read at every launch
   a.aligned16 = ((((uintptr_t)j.d1) | ((uintptr_t)j.d2)) & 15) == 0 ? 1 : 0;
-  if (tile32 && a.filter32 && smem + tile32 <= g_c.smem_optin) { a.tile32_in_smem = 1; smem += tile32; }
+  if (tile32 && a.filter32 && smem + tile32 <= g_c.smem_optin) {
+    // in shared memory when DG_LB_BLOCKS CTAs per SM still fit; otherwise the tile lives in the slab (L1/L2)
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + tile32)));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem + tile32));
+    if (occ >= DG_LB_BLOCKS) { a.tile32_in_smem = 1; smem += tile32; }
+  }
   int per_sm = 0;
   const int want_tile = cfg_smem_tile();
   if (want_tile != 0 && smem + tile <= g_c.smem_optin) {
@@ -380,7 +391,7 @@ int launch(const Job& j, cudaStream_t st, const int* d_ready = nullptr, int* d_s
   { const int cap = env_int("DGB200_CTAS_PER_SM", 0); if (cap >= 1 && cap < per_sm) per_sm = cap; }
   int grid = g_c.sm_count * per_sm;     // persistent CTAs: a whole number of CTAs per SM
   if (grid > j.n_pairs) grid = j.n_pairs;
-  a.ws_stride = dg::align_up(dg::workspace_bytes(n, a.chunk), 256);
+  a.ws_stride = dg::align_up(dg::workspace_bytes(n, a.chunk, j.laf_coef > 0 && j.dim == 6), 256);
   const size_t need = a.ws_stride * (size_t)grid;
   LaunchCtx* lc = nullptr;
   const int rc = acquire_ctx(st, need, &lc);

@@ -382,8 +382,8 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
   DG_PROF_BEGIN(1);
   DG_PROF_COUNT(13, c.sc->counter[0]);
   int ncand = c.sc->counter[0];
-  if (ncand > W.cand_cap) ncand = W.cand_cap;
   *valid_itersam = (c.sc->counter[2] != 0);
+  if (ncand > W.cand_cap) { DG_SYNC(); return -1; }   // queue overflow: the driver splits the wave
   // stage B: one warp per model, lanes stride the correspondences
   const double w94 = P.th * 9 / 4;
   #pragma unroll 1
@@ -646,7 +646,11 @@ DG_ENGN void ransac_F_pair(const Ctx& c, const FParams& P, Workspace& W, double*
     if (passall && kend > kIterSam) kend = kIterSam;
     const double T = st.maxS.J < st.maxSs.J ? st.maxS.J : st.maxSs.J;
     bool valid_itersam = false;
-    const int npass = wave_F(c, P, W, k0 + 1, kend, T, passall, &valid_itersam);
+    int npass = wave_F(c, P, W, k0 + 1, kend, T, passall, &valid_itersam);
+    while (npass < 0) {   // more oriented-valid models than the queue holds (up to 3 per iteration): halve the wave
+      kend = k0 + ((kend - k0) > 1 ? (kend - k0) / 2 : 1);
+      npass = wave_F(c, P, W, k0 + 1, kend, T, passall, &valid_itersam);
+    }
     int pos = 0;
     bool rewave = false, did_itersam = false;
     while (pos < npass) {

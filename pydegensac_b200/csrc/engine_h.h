@@ -15,8 +15,14 @@
 #include "block.h"
 #include "ffit.h"
 #include "hfit.h"
+#include "filter32.h"
 
 namespace dg {
+
+#ifdef DG_FILTER_CHECK
+static long g_hfilter_checked = 0, g_hfilter_violations = 0;
+#endif
+
 
 struct HParams {
   double th, sym_th, conf, laf_coef;
@@ -245,6 +251,50 @@ DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int k
     if (!passall) {
       double h[9];
       for (int j = 0; j < 9; ++j) h[j] = W.cand[ci].f[j];
+      if (c.t32 && P.metric == H_SAMPSON) {
+        // FP32 upper bound of the MSAC score (filter32.h): a superset of the models that matter survives
+        HFilter32 hf;
+        h_filter_setup(h, *c.t32, w94, &hf);
+        float J = 0.0f;
+#if DG_DEVICE_PASS
+        {
+          HFilter32x2 f2;
+          h_filter_pack(hf, &f2);
+          const float4* tp = reinterpret_cast<const float4*>(c.t32->pts);
+          const int npair = (c.N + 1) >> 1;
+          const int last = (c.N & 1) ? npair - 1 : -1;
+          f32x2 Ja = pk2(0.0f, 0.0f), Jb = pk2(0.0f, 0.0f);
+          int i = c.lane;
+          #pragma unroll 1
+          for (; i + 32 < npair; i += 64) {
+            const float4 A0 = tp[2 * i], B0 = tp[2 * i + 1], A1 = tp[2 * i + 64], B1 = tp[2 * i + 65];
+            Ja = add2(Ja, h_filter_gain2(f2, A0, B0, i != last));
+            Jb = add2(Jb, h_filter_gain2(f2, A1, B1, i + 32 != last));
+          }
+          if (i < npair) Ja = add2(Ja, h_filter_gain2(f2, tp[2 * i], tp[2 * i + 1], i != last));
+          float j0, j1;
+          upk2(add2(Ja, Jb), j0, j1);
+          J = j0 + j1;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) J += __shfl_xor_sync(0xffffffffu, J, o);
+        }
+#else
+        for (int i = 0; i < c.N; ++i) J += h_filter_gain(hf, c.t32->pts[i]);
+#endif
+        const double Jup = (double)J * (1.0 + 1.52587890625e-05) + 1e-3;
+#ifdef DG_FILTER_CHECK
+        {
+          double J64 = 0.0;
+          for (int i = 0; i < c.N; ++i) {
+            const double e = h_resid_sampson(h, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+            if (e < w94) J64 += 1 - (e / w94);
+          }
+          ++g_hfilter_checked;
+          if (!(Jup >= J64) && J64 == J64) ++g_hfilter_violations;
+        }
+#endif
+        keep = Jup > T - 1e-9 * (1.0 + fabs(T));
+      } else {
       HSym s;
       if (P.metric != H_SAMPSON) h_sym_prepare(h, &s);
       double J = 0.0;
@@ -258,6 +308,7 @@ DG_ENGN int wave_H(const Ctx& c, const HParams& P, Workspace& W, int kbeg, int k
       }
       J = warp_sum(J);
       keep = J > T - 1e-9 * (1.0 + fabs(T));
+      }
     }
     if (c.lane == 0 && keep) {
       const int slot = atomic_inc_shared(&c.sc->counter[1]);

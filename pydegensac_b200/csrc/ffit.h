@@ -19,7 +19,7 @@ struct Workspace {
   double* err[4];   // the reference's four residual rows errs[0..3] (physical storage)
   double* errBest;  // errorsBest
   double* w;        // LSQ weights
-  double* dtmp[8];  // scratch rows (DEGENSAC / H paths)
+  double* dtmp[6];  // scratch rows (DEGENSAC / H paths)
   double* laf[8];   // LAF helper correspondences (see Ctx::laf)
   int* inliers;
   int* intbuff;

@@ -204,4 +204,122 @@ __device__ __forceinline__ f32x2 f_filter_gain2(const FFilter32x2& f, const floa
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same idea for the HOMOGRAPHY wave with the Sampson metric (reference HDs + pinvJ, Htools.c:135-199).
+// With r = (r1, r2) the linearised residual pair and J = [a b c 0; d e 0 c] its 2 x 4 Jacobian, HDs returns
+// |J^+ r|^2 = r^T (J J^T)^-1 r  >=  |r|^2 / lambda_max(J J^T), and lambda_max has the closed form
+// (A + D)/2 + sqrt(((A - D)/2)^2 + B^2) with A = a^2+b^2+c^2, D = d^2+e^2+c^2, B = ad+be.  For the models that matter
+// (near-affine H: J J^T nearly isotropic) the inequality is nearly tight.  Both r and J are invariant under
+// translations of the two images when H is conjugated accordingly (H' = T1^-1 H T2), so the FP32 evaluation runs on
+// the centred tile of the pair, exactly as for F, with the same kind of rounding budgets:
+//   |r^_k - r_k| <= Er = 16 2^-24 K_r,   |J^ - J|_F <= 2.5 Eg,  Eg = 8 2^-24 K_g,
+//   e_lo = ((|r^_1| - Er)_+^2 + (|r^_2| - Er)_+^2) / (lambda^_max c1 + c2) (1 - 2^-17) <= e,   c2 = (2.5 Eg)^2 (1 + 2^12).
+// ~22 FP32 instructions per (model, correspondence) instead of ~300 FP64 ones (HDs has 8 FP64 divisions).
+// ---------------------------------------------------------------------------------------------------------------
+struct HFilter32 {
+  float H[9];       // centred, max-normalised, COLUMN-major like the engine's h (maps image 2 -> image 1)
+  float Er, c1, c2, winv;
+};
+DG_HD void h_filter_setup(const double* h, const Tile32& T, double w, HFilter32* o) {
+  // Hm[r][c] = h[r + 3 c];  H' = T1^-1 Hm T2  (T_k: translation by the centroid of image k)
+  double G[9], Hp[9];
+  for (int r = 0; r < 3; ++r) {
+    G[3 * r] = h[r]; G[3 * r + 1] = h[r + 3];
+    G[3 * r + 2] = h[r] * T.cen[2] + h[r + 3] * T.cen[3] + h[r + 6];
+  }
+  for (int cc = 0; cc < 3; ++cc) {
+    Hp[cc] = G[cc] - T.cen[0] * G[6 + cc];
+    Hp[3 + cc] = G[3 + cc] - T.cen[1] * G[6 + cc];
+    Hp[6 + cc] = G[6 + cc];
+  }
+  double mx = 0.0;
+  for (int i = 0; i < 9; ++i) mx = fmax(mx, fabs(Hp[i]));
+  const double sc = (mx > 0.0 && mx < 1e300) ? 1.0 / mx : 1.0;
+  double a[9];
+  for (int r = 0; r < 3; ++r)
+    for (int cc = 0; cc < 3; ++cc) { o->H[r + 3 * cc] = (float)(Hp[3 * r + cc] * sc); a[r + 3 * cc] = fabs((double)o->H[r + 3 * cc]); }
+  const double b1x = T.bnd[0], b1y = T.bnd[1], b2x = T.bnd[2], b2y = T.bnd[3];
+  const double wmag = a[2] * b2x + a[5] * b2y + a[8];
+  const double Kr1 = a[0] * b2x + a[3] * b2y + a[6] + b1x * wmag;
+  const double Kr2 = a[1] * b2x + a[4] * b2y + a[7] + b1y * wmag;
+  const double Kg = fmax(fmax(fmax(a[0] + a[2] * b1x, a[3] + a[5] * b1x), fmax(a[1] + a[2] * b1y, a[4] + a[5] * b1y)), wmag);
+  const double u24 = 5.9604644775390625e-08;   // 2^-24
+  o->Er = (float)(16.0 * u24 * fmax(Kr1, Kr2) * 1.0001);
+  const double Eg = 2.5 * 8.0 * u24 * Kg * 1.0001;
+  o->c1 = (float)((1.0 + 3.814697265625e-06) * (1.0 + 2.44140625e-04) * (1.0 + 1e-6));   // (1 + 2^-18)(1 + 2^-12), rounded up
+  o->c2 = (float)(Eg * Eg * 4097.0 * 1.0001);
+  o->winv = (float)((1.0 / w) * (1.0 - 7.62939453125e-06) * (1.0 - 1e-6));
+}
+DG_HD float h_filter_gain(const HFilter32& f, const Pt32& p) {
+#if DG_DEVICE_PASS
+#define DG_FMAF __fmaf_rn
+#define DG_RCPF(x) __fdividef(1.0f, (x))
+#define DG_SQRTF(x) __fsqrt_ru(x)
+#else
+#define DG_FMAF fmaf
+#define DG_RCPF(x) (1.0f / (x))
+#define DG_SQRTF(x) (sqrtf(x) * 1.0000002f)
+#endif
+  const float* H = f.H;
+  const float nw = -DG_FMAF(H[2], p.s, DG_FMAF(H[5], p.t, H[8]));
+  const float r1 = DG_FMAF(p.u, nw, DG_FMAF(H[0], p.s, DG_FMAF(H[3], p.t, H[6])));
+  const float r2 = DG_FMAF(p.v, nw, DG_FMAF(H[1], p.s, DG_FMAF(H[4], p.t, H[7])));
+  const float a = DG_FMAF(-H[2], p.u, H[0]), b = DG_FMAF(-H[5], p.u, H[3]);
+  const float d = DG_FMAF(-H[2], p.v, H[1]), e = DG_FMAF(-H[5], p.v, H[4]);
+  const float cc = nw * nw;
+  const float A = DG_FMAF(a, a, DG_FMAF(b, b, cc)), D = DG_FMAF(d, d, DG_FMAF(e, e, cc)), B = DG_FMAF(a, d, b * e);
+  const float hs = 0.5f * (A + D), hd = 0.5f * (A - D);
+  const float lam = hs + DG_SQRTF(DG_FMAF(hd, hd, B * B));
+  const float l1 = fmaxf(fabsf(r1) - f.Er, 0.0f), l2 = fmaxf(fabsf(r2) - f.Er, 0.0f);
+  const float e_lo = DG_FMAF(l1, l1, l2 * l2) * DG_RCPF(DG_FMAF(lam, f.c1, f.c2));
+#undef DG_FMAF
+#undef DG_RCPF
+#undef DG_SQRTF
+  const float g = 1.0f - e_lo * f.winv;
+  return g > 0.0f ? g : 0.0f;
+}
+
+#if DG_DEVICE_PASS
+struct HFilter32x2 {
+  f32x2 H0, H1, H3, H4, H6, H7, nH2, nH5, nH8;
+  f32x2 c1, c2, nwinv, one, half, mone;
+  float Er;
+};
+__device__ __forceinline__ void h_filter_pack(const HFilter32& f, HFilter32x2* o) {
+  o->H0 = pk2(f.H[0], f.H[0]); o->H1 = pk2(f.H[1], f.H[1]); o->H3 = pk2(f.H[3], f.H[3]); o->H4 = pk2(f.H[4], f.H[4]);
+  o->H6 = pk2(f.H[6], f.H[6]); o->H7 = pk2(f.H[7], f.H[7]);
+  o->nH2 = pk2(-f.H[2], -f.H[2]); o->nH5 = pk2(-f.H[5], -f.H[5]); o->nH8 = pk2(-f.H[8], -f.H[8]);
+  o->c1 = pk2(f.c1, f.c1); o->c2 = pk2(f.c2, f.c2); o->nwinv = pk2(-f.winv, -f.winv); o->one = pk2(1.0f, 1.0f);
+  o->half = pk2(0.5f, 0.5f); o->mone = pk2(-1.0f, -1.0f);
+  o->Er = f.Er;
+}
+__device__ __forceinline__ f32x2 h_filter_gain2(const HFilter32x2& f, const float4 A4, const float4 B4, bool hi_live) {
+  const f32x2 u = pk2(A4.x, A4.y), v = pk2(A4.z, A4.w), s = pk2(B4.x, B4.y), t = pk2(B4.z, B4.w);
+  const f32x2 nw = fma2(f.nH2, s, fma2(f.nH5, t, f.nH8));
+  const f32x2 r1 = fma2(u, nw, fma2(f.H0, s, fma2(f.H3, t, f.H6)));
+  const f32x2 r2 = fma2(v, nw, fma2(f.H1, s, fma2(f.H4, t, f.H7)));
+  const f32x2 a = fma2(f.nH2, u, f.H0), b = fma2(f.nH5, u, f.H3), d = fma2(f.nH2, v, f.H1), e = fma2(f.nH5, v, f.H4);
+  const f32x2 cc = mul2(nw, nw);
+  const f32x2 A = fma2(a, a, fma2(b, b, cc)), D = fma2(d, d, fma2(e, e, cc)), B = fma2(a, d, mul2(b, e));
+  const f32x2 hs = mul2(add2(A, D), f.half), hd = mul2(fma2(D, f.mone, A), f.half);
+  float q0, q1, h0, h1;
+  upk2(fma2(hd, hd, mul2(B, B)), q0, q1);
+  upk2(hs, h0, h1);
+  const f32x2 lam = pk2(h0 + __fsqrt_ru(q0), h1 + __fsqrt_ru(q1));
+  float x0, x1, y0, y1;
+  upk2(r1, x0, x1);
+  upk2(r2, y0, y1);
+  const f32x2 l1 = pk2(fmaxf(fabsf(x0) - f.Er, 0.0f), fmaxf(fabsf(x1) - f.Er, 0.0f));
+  const f32x2 l2 = pk2(fmaxf(fabsf(y0) - f.Er, 0.0f), fmaxf(fabsf(y1) - f.Er, 0.0f));
+  float d0, d1;
+  upk2(fma2(lam, f.c1, f.c2), d0, d1);
+  const f32x2 el = mul2(fma2(l1, l1, mul2(l2, l2)), pk2(__fdividef(1.0f, d0), __fdividef(1.0f, d1)));
+  float g0, g1;
+  upk2(fma2(el, f.nwinv, f.one), g0, g1);
+  g0 = fmaxf(g0, 0.0f);
+  g1 = hi_live ? fmaxf(g1, 0.0f) : 0.0f;
+  return pk2(g0, g1);
+}
+#endif
+
 }  // namespace dg

@@ -15,6 +15,7 @@ using namespace dg;
 
 static int g_use_filter32 = 1;
 extern "C" void emu_set_filter32(int on) { g_use_filter32 = on; }
+extern "C" void emu_hfilter_stats(long* checked, long* violations) { *checked = g_hfilter_checked; *violations = g_hfilter_violations; }
 extern "C" void emu_filter_stats(long* checked, long* violations, double* maxslack) {
   *checked = g_filter_checked; *violations = g_filter_violations; *maxslack = g_filter_maxslack;
 }
@@ -35,9 +36,9 @@ static int g_poison = 0;
 extern "C" void emu_set_poison(int v) { g_poison = v; }
 static void emu_setup(Emu& E, const double* x1y1, const double* x2y2, int n, int dim, int chunk) {
   memset(&E.sc, g_poison, sizeof(E.sc));
-  const size_t bytes = workspace_bytes(n, chunk);
+  const size_t bytes = workspace_bytes(n, chunk, dim == 6);
   E.slab = (unsigned char*)calloc(bytes + 256, 1);
-  workspace_carve(E.slab, n, chunk, &E.W, &E.soa);
+  workspace_carve(E.slab, n, chunk, dim == 6, &E.W, &E.soa);
   const size_t row = align_up(sizeof(double) * (size_t)n, 128) / sizeof(double);
   double* x1 = E.soa; double* y1 = E.soa + row; double* x2 = E.soa + 2 * row; double* y2 = E.soa + 3 * row;
   for (int i = 0; i < n; ++i) {
@@ -90,6 +91,7 @@ extern "C" int emu_find_homography(const double* x1y1, const double* x2y2, int n
   P.conf = conf; P.laf_coef = laf_coef; P.max_iters = max_iters; P.metric = error_type;
   P.do_laf = laf_coef > 0 ? 1 : 0; P.th_laf = laf_coef * P.th;
   P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = chunk; P.final_lsq = g_final_lsq;
+  if (g_use_filter32 && error_type == H_SAMPSON) { blk_prepare_tile32(E.c, E.tile, &E.t32); E.c.t32 = &E.t32; }
   ransac_H_pair(E.c, P, E.W, H, mask, stats);
   free(E.slab); free(E.tile);
   return 0;

@@ -34,3 +34,25 @@ def test_upper_bound_holds_and_results_unchanged(scale):
     c1, v1, slack = _stats(E)
     assert c1 - c0 > 2000, "filter was not exercised"
     assert v1 - v0 == 0, "FP32 bound fell below the FP64 score %d times" % (v1 - v0)
+
+
+@pytest.mark.parametrize("scale", [1.0, 6.0, 0.1])
+def test_homography_upper_bound_holds_and_results_unchanged(scale):
+    """Same contract for the H wave's FP32 filter (Sampson metric): J_up >= J on every scored model, identical outputs."""
+    from tests.hostemu import emu
+    from pydegensac_b200.scenes import scene_H
+    E = emu.lib()
+    ck = ctypes.c_long(); vi = ctypes.c_long()
+    E.emu_hfilter_stats(ctypes.byref(ck), ctypes.byref(vi)); c0, v0 = ck.value, vi.value
+    for sc in range(5):
+        p1, p2, _ = scene_H(1200, 130 + 40 * sc, 20 + sc)
+        p1 = p1 * scale + 2000.0 * (scale - 1.0)
+        p2 = p2 * scale - 500.0 * (scale - 1.0)
+        kw = dict(px_th=3.0 * scale, conf=0.9999, max_iters=6000, seed=sc)
+        E.emu_set_filter32(1); a = emu.find_homography_raw(p1, p2, **kw)
+        E.emu_set_filter32(0); b = emu.find_homography_raw(p1, p2, **kw)
+        E.emu_set_filter32(1)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    E.emu_hfilter_stats(ctypes.byref(ck), ctypes.byref(vi))
+    assert ck.value - c0 > 150, "filter was not exercised"
+    assert vi.value - v0 == 0, "FP32 bound fell below the FP64 score %d times" % (vi.value - v0)

@@ -300,6 +300,26 @@ def test_fp32_wave_filter_does_not_change_results(monkeypatch):
         assert np.array_equal(x, y)
 
 
+def test_fp32_wave_filter_homography(monkeypatch, ref_oracle):
+    """The H wave's FP32 filter (Sampson metric): byte-identical outputs with the filter on and off at N = 5000 (tile in
+    the slab) and N = 1200 (tile in shared memory), odd N included (padding slot of the pair-interleaved tile)."""
+    from pydegensac_b200 import _cabi
+    for (n, n_in, P) in [(5000, 1500, 24), (1201, 300, 32), (4097, 900, 8)]:
+        b1 = np.empty((P, n, 2)); b2 = np.empty((P, n, 2))
+        for i in range(P):
+            b1[i], b2[i], _ = scene_H(n, n_in, 70 + i)
+        seeds = np.arange(P, dtype=np.uint64) + 3
+        monkeypatch.delenv("DGB200_FILTER32", raising=False)
+        on = _cabi.homography_batch(b1, b2, 3.0, 0.999, 10000, 0, True, 0.0, seeds)
+        monkeypatch.setenv("DGB200_FILTER32", "0")
+        off = _cabi.homography_batch(b1, b2, 3.0, 0.999, 10000, 0, True, 0.0, seeds)
+        monkeypatch.delenv("DGB200_FILTER32")
+        for x, y in zip(on, off):
+            assert np.array_equal(x, y)
+        a = ref_oracle.find_homography_raw(b1[0], b2[0], 3.0, 0.999, 10000, seed=int(seeds[0]))
+        _cmp(a, (on[0][0], on[1][0], on[2][0]), "H n=%d" % n)
+
+
 def test_device_pointers_need_only_8_byte_alignment():
     """[n,2] inputs that are 8- but not 16-byte aligned (an offset view) take the scalar staging path."""
     import torch
