@@ -361,7 +361,7 @@ def run_gpu_arm(args):
     hn1, hn2 = hp1.numpy(), hp2.numpy()
     api = pdg.findFundamentalMatrixBatch if kind == "F" else pdg.findHomographyBatch
     if world == 1:
-        api(hn1[:64], hn2[:64], cfg["px_th"], cfg["conf"], cfg["max_iters"], seeds=seeds[:64])
+        api(hn1, hn2, cfg["px_th"], cfg["conf"], cfg["max_iters"], seeds=seeds)    # untimed warm-up step (sizes the staging buffers)
     else:
         sb.step(hp1, hp2, hseed)
     barrier()
