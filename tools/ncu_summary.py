@@ -5,7 +5,7 @@ import bisect, csv, io, re, subprocess, sys, os
 
 rep, out = sys.argv[1], sys.argv[2]
 npairs = int(sys.argv[3]) if len(sys.argv) > 3 else None
-lib = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pydegensac_b200", "libdegensac_b200.so")
+lib = os.path.abspath(sys.argv[4]) if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pydegensac_b200", "libdegensac_b200.so")
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -44,16 +44,16 @@ try:
     tmp = "/tmp/_ncu_sum"
     os.makedirs(tmp, exist_ok=True)
     subprocess.run("cd %s && rm -f *.cubin && cuobjdump -xelf all %s > /dev/null 2>&1" % (tmp, lib), shell=True)
-    cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    cub = [f for f in os.listdir(tmp) if f.endswith(".cubin") and f.startswith("degensac_b200.")][0]
     sym = subprocess.run(["readelf", "-sW", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
     kname = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else ""
     kind = "ILi1E" if "(int)1" in kname else "ILi0E"
     syms = []
     for l in sym.splitlines():
         f = l.split()
-        if len(f) >= 8 and f[3] == "FUNC" and kind in f[7]:
-            m = re.search(r"\$_ZN2dg\d+([A-Za-z_0-9]+?)E", f[7])
-            syms.append((int(f[1], 16), int(f[2], 0), m.group(1) if m else f[7][-32:]))
+        if len(f) >= 8 and f[3] == "FUNC" and kind in f[-1]:
+            m = re.search(r"\$_ZN2dg\d+([A-Za-z_0-9]+?)E", f[-1])
+            syms.append((int(f[1], 16), int(f[2], 0), m.group(1) if m else f[-1][-32:]))
     syms.sort()
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     srows = list(csv.reader(io.StringIO(src)))
@@ -87,7 +87,8 @@ try:
         t = max(1, sum(rs[k]))
         sel = max(1, rs[k][reasons.index("stall_selected")])
         lines.append("  %-30s %s  %8.1f" % (k, " ".join("%8.1f" % (100.0 * x / t) for x in rs[k]), t / sel))
-except Exception as ex:  # pragma: no cover
+except Exception as ex:
+    import traceback; traceback.print_exc()
     lines.append("(per-function breakdown unavailable: %r)" % (ex,))
 open(out, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
