@@ -47,7 +47,7 @@ try:
     cub = [f for f in os.listdir(tmp) if f.endswith(".cubin") and f.startswith("degensac_b200.")][0]
     sym = subprocess.run(["readelf", "-sW", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
     kname = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else ""
-    kind = "ILi1E" if "(int)1" in kname else "ILi0E"
+    kind = os.environ.get("NCU_KIND") or ("ILi1E" if "(int)1" in kname else "ILi0E")
     syms = []
     for l in sym.splitlines():
         f = l.split()
