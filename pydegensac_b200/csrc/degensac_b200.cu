@@ -367,8 +367,10 @@ int launch(const Job& j, cudaStream_t st, const int* d_ready = nullptr, int* d_s
   a.tile32_in_smem = 0;
   a.filter32 = (env_int("DGB200_FILTER32", 1) != 0 && (KIND == 0 || j.metric == dg::H_SAMPSON)) ? 1 : 0;   // parity switch, read at every launch
   a.aligned16 = ((((uintptr_t)j.d1) | ((uintptr_t)j.d2)) & 15) == 0 ? 1 : 0;
-  if (tile32 && a.filter32 && smem + tile32 <= g_c.smem_optin) {
-    // in shared memory when DG_LB_BLOCKS CTAs per SM still fit; otherwise the tile lives in the slab (L1/L2)
+  if (tile32 && a.filter32 && smem + tile32 <= g_c.smem_optin && env_int("DGB200_TILE32_SMEM", 0) != 0) {
+    // DGB200_TILE32_SMEM=1: the tile in shared memory (when DG_LB_BLOCKS CTAs per SM still fit).  Default: in the slab,
+    // served by L1 -- measured 1.4 % faster at N = 2000 (16.37k vs 16.15k pairs/s): the 64 KB of L1 per SM the two
+    // tiles would take are worth more to the serial steps (stack, lists, queue) than shared-memory residency to the wave
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + tile32)));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem + tile32));

@@ -308,11 +308,8 @@ DG_ENGN int wave_F(const Ctx& c, const FParams& P, Workspace& W, int kbeg, int k
                          bool* valid_itersam) {
   DG_SYNC();
   if (c.tid == 0) { c.sc->counter[0] = 0; c.sc->counter[1] = 0; c.sc->counter[2] = 0; }
-  // the minimal solvers gather 7 random correspondences per sample: pull the whole SoA (4 x N doubles) into L1 first
-  #pragma unroll 1
-  for (int i = c.tid * 16; i < c.N; i += c.nt * 16) {
-    prefetch_l1(c.x1 + i); prefetch_l1(c.y1 + i); prefetch_l1(c.x2 + i); prefetch_l1(c.y2 + i);
-  }
+  // (an L1 prefetch of the whole SoA in front of the gathers of stage A was measured neutral-to-negative once the
+  //  streaming passes stopped polluting L1 -- the lines it displaced, stack and lists, cost as much as it saved)
   DG_SYNC();
   // stage A: minimal solvers.  Device: A1 = two threads per sample eliminate in registers (wave_F_pairsolve),
   // A2 = one thread per sample takes the null-space basis through the cubic and the oriented test.
