@@ -10,8 +10,19 @@
 
 namespace dg {
 
-constexpr int kMaxWarps = 16;      // CTA size <= 512
+constexpr int kMaxWarps = 16;      // group size <= 512 threads
 constexpr int kVecRed = 48;        // widest vector reduction (45 covariance entries)
+// warps of one group as far as the scratch layout is concerned (both nvcc passes must agree on sizeof(BlockScratch);
+// the one-thread host emulation keeps the full layout)
+#if defined(__CUDACC__)
+constexpr int kGroupWarpsScratch = DG_GROUP_WARPS;
+#else
+constexpr int kGroupWarpsScratch = kMaxWarps;
+#endif
+// `vec` doubles as the row buffer of the one-warp small fits (hfit.h: 2 x 32 DLT rows of 9) and as the swap-partner
+// buffer of the plane-and-parallax waves, hence the floor of 576 doubles.
+constexpr int kVecDoubles = (kGroupWarpsScratch >= 8 ? kMaxWarps : kGroupWarpsScratch) * kVecRed > 576
+                                ? (kGroupWarpsScratch >= 8 ? kMaxWarps : kGroupWarpsScratch) * kVecRed : 576;
 
 struct BlockScratch {
   double red_d[kMaxWarps];
@@ -20,10 +31,12 @@ struct BlockScratch {
   double bc[32];                   // broadcast area for small results (models, scalars)
   int bci[16];
   int counter[4];                  // atomic counters of the hypothesis wave
+  int pair, ok;                    // the group's current image pair / "its input has landed" flag
+  int stats[4];
   WarpScratch ws[1];               // warp 0's tile for the cooperative 9x9 / 8x9 solves
   union {                          // never live at the same time:
-    WarpScratch wsx[4];            //   tiles of warps 1..4 (the five checksample triplets run side by side)
-    double vec[kMaxWarps * kVecRed];   // per-warp slots of the wide block reductions
+    WarpScratch wsx[kGroupWarpsScratch >= 5 ? 4 : 1];   //   tiles of warps 1..4 (the five checksample triplets run side by side)
+    double vec[kVecDoubles];       //   per-warp slots of the wide block reductions
   };
   DG_ENG WarpScratch* warp_tile(int wid) { return wid == 0 ? &ws[0] : &wsx[wid - 1]; }
 };
@@ -206,6 +219,29 @@ __device__ __noinline__ void blk_inlidxs_ballot(const Ctx& c, const double* __re
     wq[t] = th[t] * 9 / 4;
     winv[t] = (th[t] == 0) ? 0.0 : 1.0 / wq[t];
     J[t] = 0.0; off[t] = 0; cnt[t] = 0; parked[t] = 0u;
+  }
+  if (c.nw == 1) {   // one warp owns the row: single pass, running offsets
+    #pragma unroll 1
+    for (int base = 0; base < c.N; base += 64) {
+      const int i0 = base + c.lane, i1 = i0 + 32;
+      const double e0 = (i0 < c.N) ? ld_row(err + i0) : INFINITY;
+      const double e1 = (i1 < c.N) ? ld_row(err + i1) : INFINITY;
+#pragma unroll
+      for (int t = 0; t < NTH; ++t) {
+        if (th[t] != 0 && !(e0 >= wq[t])) J[t] += 1 - e0 * winv[t];
+        if (th[t] != 0 && !(e1 >= wq[t])) J[t] += 1 - e1 * winv[t];
+        const bool in0 = e0 <= th[t], in1 = e1 <= th[t];
+        const unsigned m0 = __ballot_sync(full, in0), m1 = __ballot_sync(full, in1);
+        const int o1 = off[t] + __popc(m0);
+        if (in0) lists[t][off[t] + __popc(m0 & lt)] = i0;
+        if (in1) lists[t][o1 + __popc(m1 & lt)] = i1;
+        off[t] = o1 + __popc(m1);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < NTH; ++t) { S[t] = make_score(); S[t].J = warp_sum(J[t]); S[t].I = (unsigned)off[t]; }
+    __syncwarp();
+    return;
   }
   const int chunk = (((c.N + c.nw - 1) / c.nw) + 31) & ~31;
   const int wbeg = c.wid * chunk;

@@ -97,23 +97,30 @@ struct BatchArgs {
 template <int KIND>  // 0: fundamental matrix, 1: homography
 __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel(BatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_pair;
-  dg::BlockScratch* sc = reinterpret_cast<dg::BlockScratch*>(smem_raw);
+  // The CTA hosts blockDim.x / GT groups (one in the default build); each owns one pair at a time, its own scratch,
+  // slab and barrier.
+  constexpr int GT = (DG_GROUP_WARPS == DG_CTA_WARPS) ? 0 : 32 * DG_GROUP_WARPS;   // 0: the group is the whole CTA
+  const int gthreads = GT ? GT : (int)blockDim.x;
+  const int gid = GT ? (int)threadIdx.x / GT : 0, ngroups = GT ? (int)blockDim.x / GT : 1;
+  const int gtid = GT ? (int)threadIdx.x % GT : (int)threadIdx.x;
   const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128);
+  dg::BlockScratch* sc = reinterpret_cast<dg::BlockScratch*>(smem_raw + (size_t)gid * sc_bytes);
+  unsigned char* slab = a.workspace + ((size_t)blockIdx.x * ngroups + gid) * a.ws_stride;
   dg::Workspace W;
   double* soa_global;
   const bool use_laf = (a.laf_coef > 0) && (a.dim == 6);
-  dg::workspace_carve(a.workspace + (size_t)blockIdx.x * a.ws_stride, a.n, a.chunk, use_laf, &W, &soa_global);
+  dg::workspace_carve(slab, a.n, a.chunk, use_laf, &W, &soa_global);
   const size_t row = dg::align_up(sizeof(double) * (size_t)a.n, 128) / sizeof(double);
   double* soa = a.pts_in_smem ? reinterpret_cast<double*>(smem_raw + sc_bytes) : soa_global;
   const size_t soa_smem_bytes = a.pts_in_smem ? dg::align_up(sizeof(double) * (size_t)a.n, 128) * 4 : 0;
   dg::Pt32* tile32 = a.tile32_in_smem
-                         ? reinterpret_cast<dg::Pt32*>(smem_raw + sc_bytes + soa_smem_bytes)
-                         : reinterpret_cast<dg::Pt32*>(dg::workspace_tile32(a.workspace + (size_t)blockIdx.x * a.ws_stride, a.n, a.chunk, use_laf));
+                         ? reinterpret_cast<dg::Pt32*>(smem_raw + (size_t)ngroups * sc_bytes + soa_smem_bytes +
+                                                       (size_t)gid * dg::align_up(16 * ((size_t)a.n + 1), 128))
+                         : reinterpret_cast<dg::Pt32*>(dg::workspace_tile32(slab, a.n, a.chunk, use_laf));
   dg::Tile32 t32;
 
   dg::Ctx c;
-  c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5;
+  c.tid = gtid; c.nt = gthreads; c.lane = gtid & 31; c.wid = gtid >> 5; c.nw = gthreads >> 5;
   c.N = a.n;
   c.x1 = soa; c.y1 = soa + row; c.x2 = soa + 2 * row; c.y2 = soa + 3 * row;
   c.sc = sc;
@@ -121,18 +128,17 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
   for (int i = 0; i < 8; ++i) c.laf[i] = use_laf ? W.laf[i] : nullptr;
 
   for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_pair = atomicAdd(a.work_counter, 1);
-    __syncthreads();
-    const int p = s_pair;
+    DG_SYNC();
+    if (gtid == 0) sc->pair = atomicAdd(a.work_counter, 1);
+    DG_SYNC();
+    const int p = sc->pair;
     if (p >= a.n_pairs) break;
     if (a.ready) {
       // The host streams the batch in chunks on a copy stream while this kernel runs and bumps `ready` after each
       // chunk.  The wait is bounded: when copies cannot overlap the kernel (a profiler serialising the streams, a
       // stalled link) the CTA records the pair, raises the abort flag and retires; the host then runs the pairs from
       // the smallest recorded index on in a second, ordinary launch.  Nothing can hang.
-      __shared__ int s_ok;
-      if (threadIdx.x == 0) {
+      if (gtid == 0) {
         int ok = (*reinterpret_cast<volatile int*>(a.status) == 0) ? 1 : 0;
         if (ok) {
           const long long t0 = clock64();
@@ -142,10 +148,10 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
           }
         }
         if (!ok) { atomicMin(a.status + 1, p); atomicExch(a.status, 1); }
-        s_ok = ok;
+        sc->ok = ok;
       }
-      __syncthreads();
-      if (!s_ok) break;
+      DG_SYNC();
+      if (!sc->ok) break;
     }
     // ---- stage the pair: HBM -> SoA tile (the only read of the pair from HBM)
     const size_t row0 = a.offsets ? (size_t)a.offsets[p] : (size_t)p * a.n;
@@ -156,12 +162,12 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
     if (a.dim == 2 && a.aligned16) {   // rows are 16 bytes, so every pair of a ragged batch starts aligned too
       const double2* v1 = reinterpret_cast<const double2*>(g1);
       const double2* v2 = reinterpret_cast<const double2*>(g2);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      for (int i = gtid; i < n; i += gthreads) {
         const double2 q1 = __ldcg(v1 + i), q2 = __ldcg(v2 + i);   // L2 only: the chunk may have landed after this kernel started
         soa[i] = q1.x; soa[row + i] = q1.y; soa[2 * row + i] = q2.x; soa[3 * row + i] = q2.y;
       }
     } else {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      for (int i = gtid; i < n; i += gthreads) {
         const double* q1 = g1 + (size_t)i * a.dim;
         const double* q2 = g2 + (size_t)i * a.dim;
         soa[i] = __ldcg(q1); soa[row + i] = __ldcg(q1 + 1);
@@ -172,12 +178,12 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
         }
       }
     }
-    __syncthreads();
+    DG_SYNC();
     const unsigned long long seed = a.seeds ? a.seeds[p] : (unsigned long long)p;
     double* model = a.model_out + (size_t)p * 9;
     unsigned char* mask = a.mask_out + row0;
     int local_stats[4];
-    __shared__ int s_stats[4];
+    int* s_stats = sc->stats;
     if (KIND == 0) {
       c.t32 = nullptr;
       if (a.filter32) {
@@ -205,13 +211,13 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
       P.final_lsq = (a.flags & DGB200_FLAG_FINAL_LSQ) ? 1 : 0;
       dg::ransac_H_pair(c, P, W, model, mask, s_stats);
     }
-    __syncthreads();
+    DG_SYNC();
     // "no model" convention of the Python layer (utils.py:104-107, 143-145): zero model -> empty mask
     double asum = 0.0;
     for (int i = 0; i < 9; ++i) asum += fabs(model[i]);
     if (asum == 0.0)
-      for (int i = threadIdx.x; i < n; i += blockDim.x) mask[i] = 0;
-    if (a.stats_out && threadIdx.x < 4) a.stats_out[(size_t)p * 4 + threadIdx.x] = s_stats[threadIdx.x];
+      for (int i = gtid; i < n; i += gthreads) mask[i] = 0;
+    if (a.stats_out && gtid < 4) a.stats_out[(size_t)p * 4 + gtid] = s_stats[gtid];
     (void)local_stats;
   }
 }
@@ -354,10 +360,11 @@ int launch(const Job& j, cudaStream_t st, const int* d_ready = nullptr, int* d_s
   a.model_out = j.d_model; a.mask_out = j.d_mask; a.stats_out = j.d_stats;
   a.chunk = kChunk;
   const int n = j.n;
-  const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128);
+  constexpr int kGroups = DG_CTA_WARPS / DG_GROUP_WARPS;                      // pairs side by side per CTA (1 by default)
+  const size_t sc_bytes = dg::align_up(sizeof(dg::BlockScratch), 128) * kGroups;
   const size_t tile = dg::align_up(sizeof(double) * (size_t)n, 128) * 4;       // FP64 SoA of the pair
-  const size_t tile32 = (16 * ((size_t)n + 1) <= 98304) ? dg::align_up(16 * ((size_t)n + 1), 128) : 0;   // FP32 filter tile (pair-interleaved: N+1 slots)
-  const int kThreads = cfg_threads();
+  const size_t tile32 = (16 * ((size_t)n + 1) <= 98304) ? dg::align_up(16 * ((size_t)n + 1), 128) * kGroups : 0;   // FP32 filter tile(s) (pair-interleaved: N+1 slots)
+  const int kThreads = (kGroups > 1) ? 32 * DG_CTA_WARPS : cfg_threads();
   auto kern = ransac_pairs_kernel<KIND>;
   // Shared-memory plan: block scratch always; the FP32 filter tile when it fits.  The FP64 correspondences stay in
   // global memory (L1/L2-resident): DGB200_SMEM_TILE=1 moves them to shared memory too, which measured 12 % slower
@@ -378,7 +385,7 @@ int launch(const Job& j, cudaStream_t st, const int* d_ready = nullptr, int* d_s
   }
   int per_sm = 0;
   const int want_tile = cfg_smem_tile();
-  if (want_tile != 0 && smem + tile <= g_c.smem_optin) {
+  if (want_tile != 0 && kGroups == 1 && smem + tile <= g_c.smem_optin) {
     const size_t smem_full = smem + tile;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full));
     int occ = 0;
@@ -392,9 +399,9 @@ int launch(const Job& j, cudaStream_t st, const int* d_ready = nullptr, int* d_s
   if (per_sm < 1) return fail(DGB200_E_CUDA, "kernel does not fit on an SM");
   { const int cap = env_int("DGB200_CTAS_PER_SM", 0); if (cap >= 1 && cap < per_sm) per_sm = cap; }
   int grid = g_c.sm_count * per_sm;     // persistent CTAs: a whole number of CTAs per SM
-  if (grid > j.n_pairs) grid = j.n_pairs;
+  if ((long long)grid * kGroups > j.n_pairs) grid = (j.n_pairs + kGroups - 1) / kGroups;
   a.ws_stride = dg::align_up(dg::workspace_bytes(n, a.chunk, j.laf_coef > 0 && j.dim == 6), 256);
-  const size_t need = a.ws_stride * (size_t)grid;
+  const size_t need = a.ws_stride * (size_t)grid * kGroups;
   LaunchCtx* lc = nullptr;
   const int rc = acquire_ctx(st, need, &lc);
   if (rc) return rc;
@@ -483,7 +490,7 @@ int run_host(const double* x1y1, const double* x2y2, const int32_t* offsets, int
   // persistent CTAs wait on it before staging a pair.  Chunk 0 covers the pairs the CTAs start with.
   cudaStream_t st = g_c.s_run, cs = g_c.s_copy;
   int nchunks = 8;
-  int first = 2 * DG_LB_BLOCKS * g_c.sm_count;   // two pairs per resident CTA
+  int first = 2 * DG_LB_BLOCKS * g_c.sm_count * (DG_CTA_WARPS / DG_GROUP_WARPS);   // two pairs per resident group
   if (first > n_pairs) first = n_pairs;
   int rest = n_pairs - first;
   if (rest <= 0) nchunks = 1;
