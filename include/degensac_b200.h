@@ -157,6 +157,9 @@ int dgb200_pose_from_fundamental_batch_dev(const double* d_F, const double* d_K1
 /* The reference's alternative 7-point null-space solver nullspace_qr7x9 (Ftools.c:594-668, compile-time USE_QR,
  * exp_ranF.c:1346-1349) over `count` systems: d_A [count][7*9] row-major -> d_N [count][2*9], d_rc [count] or NULL. */
 int dgb200_nullspace_qr7x9_batch_dev(const double* d_A, double* d_N, int32_t* d_rc, int count, void* stream);
+/* Test hook: compares `count` random quotients of the shared-reciprocal division used by the homography Sampson residual
+ * (csrc/hgeom.h: h_pinvJ) bit for bit with IEEE division on the device; *h_bad = number of mismatches (must be 0). */
+int dgb200_debug_div_check(unsigned long long seed, long long count, unsigned long long* h_bad);
 const char* dgb200_frontend_last_error(void);
 
 /* Housekeeping */

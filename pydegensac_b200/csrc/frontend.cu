@@ -17,6 +17,8 @@
 #include "../../include/degensac_b200.h"
 #include "common.h"
 #include "la.h"
+#include "hgeom.h"
+#include "rng.h"
 
 namespace {
 
@@ -341,9 +343,42 @@ __global__ void qr7x9_kernel(const double* A, double* N, int* rc, int count) {
   if (rc) rc[i] = r;
 }
 
+// ------------------------------------------------------------------------------------------------ division check
+// Bit-for-bit comparison of the shared-reciprocal quotients used by h_pinvJ (hgeom.h) with IEEE division on random
+// operands spanning 60 binary orders of magnitude; returns the number of mismatches in *bad.
+__global__ void div_check_kernel(unsigned long long seed, long long count, unsigned long long* bad) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long local = 0;
+  for (long long i = i0; i < count; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t o[4];
+    dg::philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 7u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    // mantissas from 52 random bits, exponents in [-30, 30], random signs
+    const unsigned long long mx = ((unsigned long long)o[0] << 20) ^ o[1], mn = ((unsigned long long)o[2] << 20) ^ o[3];
+    const int ex = (int)(o[1] % 61u) - 30, en = (int)(o[3] % 61u) - 30;
+    double x = __longlong_as_double((long long)(((unsigned long long)(1023 + ex) << 52) | (mx & 0xfffffffffffffull)));
+    double n = __longlong_as_double((long long)(((unsigned long long)(1023 + en) << 52) | (mn & 0xfffffffffffffull)));
+    if (o[0] & 1u) x = -x;
+    if (o[2] & 1u) n = -n;
+    const double q = dg::div_by_shared_rcp(x, n, __drcp_rn(n));
+    if (__double_as_longlong(q) != __double_as_longlong(x / n)) ++local;
+  }
+  if (local) atomicAdd(bad, local);
+}
+
 }  // namespace
 
 extern "C" {
+
+int dgb200_debug_div_check(unsigned long long seed, long long count, unsigned long long* h_bad) {
+  unsigned long long* d = nullptr;
+  CU2(cudaMalloc(&d, sizeof(unsigned long long)));
+  CU2(cudaMemset(d, 0, sizeof(unsigned long long)));
+  div_check_kernel<<<1184, 256>>>(seed, count, d);
+  CU2(cudaGetLastError());
+  CU2(cudaMemcpy(h_bad, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}
 
 const char* dgb200_frontend_last_error(void) { return g_err2; }
 

@@ -341,3 +341,16 @@ def test_device_pointers_need_only_8_byte_alignment():
         torch.cuda.synchronize()
         res.append((F.cpu().numpy(), m.cpu().numpy()))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+def test_shared_reciprocal_division_is_ieee_exact():
+    """h_pinvJ divides its eight entries by one denominator through a shared correctly rounded reciprocal + two FMA
+    corrections; the quotients must be bit-identical to IEEE division (10^8 random operand pairs on the device)."""
+    import ctypes
+    from pydegensac_b200 import _cabi
+    L = _cabi.lib()
+    L.dgb200_debug_div_check.argtypes = [ctypes.c_ulonglong, ctypes.c_longlong, ctypes.POINTER(ctypes.c_ulonglong)]
+    for seed in (1, 2):
+        bad = ctypes.c_ulonglong(123)
+        assert L.dgb200_debug_div_check(seed, 100_000_000, ctypes.byref(bad)) == 0
+        assert bad.value == 0, "%d of 1e8 quotients differ from IEEE division" % bad.value
