@@ -57,9 +57,23 @@ def build_pybind(force=False):
     return out
 
 
+LEGACY = os.path.join(HERE, "libdegensac_b200_legacy.so")
+
+
+def build_legacy(force=False):
+    """The reference's own C entry points (include/degensac_legacy.h) over the C ABI."""
+    src = os.path.join(CSRC, "legacy_shim.cpp")
+    if not force and os.path.exists(LEGACY) and os.path.getmtime(LEGACY) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return LEGACY
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", src, "-o", LEGACY, "-L" + HERE,
+                           "-ldegensac_b200", "-Wl,-rpath,$ORIGIN"])
+    return LEGACY
+
+
 def build_all(force=False, verbose=False):
     build_cuda(force, verbose)
     build_pybind(force)
+    build_legacy(force)
 
 
 if __name__ == "__main__":

@@ -23,6 +23,7 @@
 #include "rng.h"
 #include "la.h"
 #include "fgeom.h"
+#include "hgeom.h"
 #include "block.h"
 #include "ffit.h"
 #include "hfit.h"
@@ -225,6 +226,11 @@ __device__ __forceinline__ void pairsolve_step(double (&a)[5][7], int h, int lan
     }
   }
   const double p = __shfl_sync(full, a[lc][COL], src);
+  // the pivot row is divided by p entry by entry (utools.c: nullspace): one correctly rounded reciprocal + two FMA
+  // corrections per quotient give the IEEE quotient bit for bit (hgeom.h: div_by_shared_rcp) at a quarter of the cost
+  const double ap = fabs(p);
+  const bool fastdiv = ap > 1e-100 && ap < 1e100;
+  const double rp = fastdiv ? __drcp_rn(p) : 0.0;
   double m[7];
 #pragma unroll
   for (int r = 0; r < 7; ++r) m[r] = (r == COL) ? 0.0 : __shfl_sync(full, a[lc][r], src);
@@ -232,7 +238,9 @@ __device__ __forceinline__ void pairsolve_step(double (&a)[5][7], int h, int lan
   for (int q = 0; q < 5; ++q) {
     const int gc = 5 * h + q;
     if (gc >= COL && gc < 9) {
-      a[q][COL] /= p;
+      const double x = a[q][COL], ax = fabs(x);
+      if (fastdiv && (ax == 0.0 || (ax > 1e-100 && ax < 1e100))) a[q][COL] = div_by_shared_rcp(x, p, rp);
+      else a[q][COL] = x / p;
 #pragma unroll
       for (int r = 0; r < 7; ++r)
         if (r != COL) a[q][r] -= m[r] * a[q][COL];
