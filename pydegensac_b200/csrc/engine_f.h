@@ -23,7 +23,6 @@
 #include "rng.h"
 #include "la.h"
 #include "fgeom.h"
-#include "hgeom.h"
 #include "block.h"
 #include "ffit.h"
 #include "hfit.h"
@@ -226,11 +225,8 @@ __device__ __forceinline__ void pairsolve_step(double (&a)[5][7], int h, int lan
     }
   }
   const double p = __shfl_sync(full, a[lc][COL], src);
-  // the pivot row is divided by p entry by entry (utools.c: nullspace): one correctly rounded reciprocal + two FMA
-  // corrections per quotient give the IEEE quotient bit for bit (hgeom.h: div_by_shared_rcp) at a quarter of the cost
-  const double ap = fabs(p);
-  const bool fastdiv = ap > 1e-100 && ap < 1e100;
-  const double rp = fastdiv ? __drcp_rn(p) : 0.0;
+  // (dividing the pivot row through one shared reciprocal, as hgeom.h does for pinvJ, was measured 1.7 % SLOWER here:
+  //  at most five quotients per thread share the reciprocal and the range guards cost more than they save)
   double m[7];
 #pragma unroll
   for (int r = 0; r < 7; ++r) m[r] = (r == COL) ? 0.0 : __shfl_sync(full, a[lc][r], src);
@@ -238,9 +234,7 @@ __device__ __forceinline__ void pairsolve_step(double (&a)[5][7], int h, int lan
   for (int q = 0; q < 5; ++q) {
     const int gc = 5 * h + q;
     if (gc >= COL && gc < 9) {
-      const double x = a[q][COL], ax = fabs(x);
-      if (fastdiv && (ax == 0.0 || (ax > 1e-100 && ax < 1e100))) a[q][COL] = div_by_shared_rcp(x, p, rp);
-      else a[q][COL] = x / p;
+      a[q][COL] /= p;
 #pragma unroll
       for (int r = 0; r < 7; ++r)
         if (r != COL) a[q][r] -= m[r] * a[q][COL];
