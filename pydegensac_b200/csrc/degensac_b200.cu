@@ -1,14 +1,19 @@
 // degensac_b200.cu -- sm_100a kernel + C ABI (include/degensac_b200.h) of the LO-RANSAC / DEGENSAC engine.
 //
-// One persistent CTA processes one image pair at a time (pairs are claimed from an atomic work counter):
-//   * the pair's correspondences are read once from HBM (coalesced 16-byte loads of the [n][dim] rows)
-//     and de-interleaved into a structure-of-arrays tile in shared memory (4 x n doubles);
-//   * engine_f.h / engine_h.h run the speculative hypothesis WAVES (thread per minimal sample, warp per
-//     scored model) and the ordered REPLAY (LO, DEGENSAC, termination) entirely on that tile;
-//   * residual rows, index lists, the hypothesis queue and the LO hash table live in a per-CTA slab of
-//     global memory that stays L2 resident.
-// All arithmetic on the path is FP64 compiled with -fmad=false so residuals, scores and solves round
-// exactly like the reference's x86-64 (no-FMA) build; there is no tensor-core work and no CPU fallback.
+// One persistent CTA (256 threads, two per SM) processes one image pair at a time; pairs are claimed from an atomic
+// work counter:
+//   * the pair's correspondences are read ONCE from HBM (coalesced 16-byte loads of the [n][dim] rows) and
+//     de-interleaved into a structure-of-arrays copy (4 x n doubles) in the CTA's slab of global memory -- L1/L2
+//     resident; shared-memory residency measured slower, see the launch plan below -- plus the centred FP32 tile of the
+//     wave filter (pair-interleaved, 16 B per correspondence);
+//   * engine_f.h / engine_h.h run the speculative hypothesis WAVES (two threads per 7-point sample / one per 4-point
+//     sample, one warp per scored model, FP32 upper-bound filter with packed FFMA2) and the ordered REPLAY (LO, DEGENSAC,
+//     termination) in exact FP64;
+//   * residual rows, index lists, the hypothesis queue and the LO hash table live in the same slab; shared memory holds
+//     only the block scratch (reductions, warp tiles of the small solves).
+// Every launch in flight owns its slabs and work counter (pool keyed by stream): the device entry points are re-entrant.
+// All FP64 arithmetic on the path is compiled with -fmad=false so residuals, scores and solves round exactly like the
+// reference's x86-64 (no-FMA) build; there is no tensor-core work and no CPU fallback.
 #include <cuda_runtime.h>
 #include <mutex>
 #include <vector>

@@ -354,3 +354,29 @@ def test_shared_reciprocal_division_is_ieee_exact():
         bad = ctypes.c_ulonglong(123)
         assert L.dgb200_debug_div_check(seed, 100_000_000, ctypes.byref(bad)) == 0
         assert bad.value == 0, "%d of 1e8 quotients differ from IEEE division" % bad.value
+
+
+def test_large_and_extreme_sizes(ref_oracle):
+    """N far beyond the benchmark sizes (rows longer than 8 residuals per thread, FP32 tile in the slab, queue sizes) and
+    the smallest legal inputs."""
+    from pydegensac_b200 import _cabi
+    p1, p2, _ = scene_F(20000, 0.35, 11)
+    a = ref_oracle.find_fundamental(p1, p2, 1.0, 0.999, 2000, seed=5)
+    F, m, s = _cabi.fundamental_batch(p1, p2, 1.0, 0.999, 2000, 0, True, 0.0, True, [5])
+    _cmp(a, (F[0], m[0], s[0]), "F n=20000")
+    q1, q2, _ = scene_H(30000, 9000, 12)
+    a = ref_oracle.find_homography_raw(q1, q2, 2.0, 0.999, 1000, seed=6)
+    H, m, s = _cabi.homography_batch(q1, q2, 2.0, 0.999, 1000, 0, True, 0.0, [6])
+    _cmp(a, (H[0], m[0], s[0]), "H n=30000")
+    # 70000 correspondences: beyond the 16-bit packed counters of the two-threshold compaction
+    r1, r2, _ = scene_F(70000, 0.5, 13)
+    F, m, s = _cabi.fundamental_batch(r1, r2, 1.0, 0.99, 300, 0, True, 0.0, True, [7])
+    a = ref_oracle.find_fundamental(r1, r2, 1.0, 0.99, 300, seed=7)
+    _cmp(a, (F[0], m[0], s[0]), "F n=70000")
+    # minimum sizes: the calls must succeed and agree between batch positions
+    t1, t2, _ = scene_F(8, 1.0, 3)
+    F8, m8, _ = _cabi.fundamental_batch(np.stack([t1, t1]), np.stack([t2, t2]), 1.0, 0.99, 200, 0, True, 0.0, True, [1, 1])
+    assert np.array_equal(F8[0], F8[1]) and np.array_equal(m8[0], m8[1])
+    h1, h2, _ = scene_H(4, 4, 3)
+    H4, m4, _ = _cabi.homography_batch(np.stack([h1, h1]), np.stack([h2, h2]), 1.0, 0.99, 200, 0, True, 0.0, [1, 1])
+    assert np.array_equal(H4[0], H4[1]) and np.array_equal(m4[0], m4[1])

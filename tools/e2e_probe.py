@@ -15,3 +15,9 @@ for name, (a1, a2) in {"pinned": (h1, h2), "pageable": (b1, b2)}.items():
         _cabi.fundamental_batch(a1, a2, 1.0, 0.9999, 10000, 0, True, 0.0, True, seeds)
         w = time.perf_counter() - t
         print(name, "wall %.1f ms, kernel %.1f ms, launches %d" % (w * 1e3, _cabi.last_kernel_ms(), _cabi.kernel_launches()), flush=True)
+import pydegensac_b200 as pdg
+for rep in range(3):
+    t = time.perf_counter()
+    F, m = pdg.findFundamentalMatrixBatch(h1, h2, 1.0, 0.9999, 10000, seeds=seeds)
+    w = time.perf_counter() - t
+    print("public API (pinned) wall %.1f ms, kernel %.1f ms" % (w * 1e3, _cabi.last_kernel_ms()), flush=True)
