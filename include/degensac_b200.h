@@ -125,6 +125,18 @@ int dgb200_find_homography_ragged_dev(const double* d_x1y1, const double* d_x2y2
                                       int sym_check, double laf_coef, const uint64_t* d_seeds,
                                       double* d_H_out, uint8_t* d_mask_out, int32_t* d_stats_out, void* stream);
 
+/* Homography from correspondences of local ELLIPTICAL features: the reference's ransacH2el (ranH2el.c:19-208; no binding
+ * in the reference -- the solver its C core carries for two-correspondence samples).  u10: [n_pairs][n][10] rows
+ * (x', y', a', b', c', x, y, a, b, c) as ranH2el.h:4 (image 1 first; each local frame the lower-triangular affinity
+ * [a 0; b c] at (x, y)).  th = px_th^2 on the Sampson error of the centres, do_lo = 1, inlLimit = 0.  H_out: RAW core
+ * output like dgb200_find_homography (column-major; inv(H^T) maps (x', y') -> (x, y)).  stats: {samples, LO runs, 0,
+ * inliers of the returned model}. */
+int dgb200_find_homography_2el_batch(const double* u10, int n_pairs, int n, double px_th, double conf, int max_iters,
+                                     const uint64_t* seeds, double* H_out, uint8_t* mask_out, int32_t* stats_out);
+int dgb200_find_homography_2el_batch_dev(const double* d_u10, int n_pairs, int n, double px_th, double conf,
+                                         int max_iters, const uint64_t* d_seeds, double* d_H_out, uint8_t* d_mask_out,
+                                         int32_t* d_stats_out, void* stream);
+
 /* One pair (what one findFundamentalMatrix_/findHomography_ call does): batch of 1 with one seed. */
 int dgb200_find_fundamental(const double* x1y1, const double* x2y2, int n, int dim, double px_th, double conf,
                             int max_iters, int error_type, int sym_check, double laf_coef, int degen_check,

@@ -58,6 +58,13 @@ def _declare(_lib):
         _lib.ref_value31.restype = ctypes.c_uint32
         _lib.ref_stateless_sample.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
                                               ctypes.POINTER(ctypes.c_int)]
+        if hasattr(_lib, "ref_find_homography_2el"):
+            _lib.ref_find_homography_2el.argtypes = [dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                                     ctypes.c_int, ctypes.c_uint64, dp, ctypes.POINTER(ctypes.c_ubyte),
+                                                     ctypes.POINTER(ctypes.c_int)]
+            _lib.ref_find_homography_2el.restype = ctypes.c_int
+            _lib.ref_h_from_2el.argtypes = [dp, dp, dp]
+            _lib.ref_h_from_2el.restype = ctypes.c_int
     return _lib
 
 
@@ -113,3 +120,27 @@ def find_homography(*a, **k):
     if np.abs(H).sum() == 0:
         return H, np.zeros_like(mask), stats
     return np.linalg.inv(H.T), mask, stats
+
+
+def find_homography_2el_raw(u10, px_th=1.0, conf=0.999, max_iters=50000, seed=0, rng=RNG_PHILOX):
+    """Reference ransacH2el (ranH2el.c:19) on rows (x', y', a', b', c', x, y, a, b, c); th = px_th^2. RAW output."""
+    u = np.ascontiguousarray(u10, dtype=np.float64)
+    n = u.shape[0]
+    assert u.shape[1] == 10
+    H = np.zeros(9, dtype=np.float64)
+    mask = np.zeros(n, dtype=np.uint8)
+    stats = np.zeros(4, dtype=np.int32)
+    rc = lib().ref_find_homography_2el(_dptr(u), n, px_th, conf, int(max_iters), int(rng), ctypes.c_uint64(int(seed)),
+                                       _dptr(H), mask.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
+                                       stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    if rc != 0:
+        raise ValueError("reference rejected the input (rc=%d)" % rc)
+    return H.reshape(3, 3), mask.astype(bool), stats
+
+
+def h_from_2el(ua, ub):
+    """Reference A2toRH (ranH2el.c:233) on two rows; returns (ok, h[9])."""
+    ua = np.ascontiguousarray(ua, dtype=np.float64); ub = np.ascontiguousarray(ub, dtype=np.float64)
+    h = np.zeros(9)
+    ok = lib().ref_h_from_2el(_dptr(ua), _dptr(ub), _dptr(h))
+    return bool(ok), h

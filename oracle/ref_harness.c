@@ -244,3 +244,37 @@ int ref_find_homography(const double *x1y1, const double *x2y2, int n, int dim, 
   g_mode = 0;
   return 0;
 }
+
+/* ---- homography from elliptical features: ransacH2el (ranH2el.c:19), no binding in the reference; rows u10 =
+ * (x', y', a', b', c', x, y, a, b, c).  The driver has no pre-loop srand(): one is issued here so that its first pass is
+ * iteration k = 1 of the stream contract like the other two drivers.  th = px_th^2 (Sampson error, as error_type 0). */
+extern RefScore ransacH2el(double *u10, int len, double th, double conf, int max_sam, double *H, unsigned char *inl,
+                           int *data_out, int do_lo, int inlLimit);
+extern int A2toRH(double *N1, double *D1, double *N2, double *D2, double *u, int *samidx, double *h);
+extern void getTransf(double *u10, double *N, double *D);
+int ref_find_homography_2el(const double *u10, int n, double px_th, double conf, int max_iters, int rng_mode,
+                            uint64_t seed, double *H_out, unsigned char *mask_out, int *stats_out) {
+  int i, data_out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double H[9], *u;
+  RefScore S;
+  if (n < 4) return -1;
+  u = (double *)malloc(sizeof(double) * 10 * (size_t)n);
+  memcpy(u, u10, sizeof(double) * 10 * (size_t)n);
+  for (i = 0; i < 9; ++i) H[i] = 0.0;
+  memset(mask_out, 0, (size_t)n);
+  rng_begin(rng_mode, seed, n, 2);
+  if (rng_mode) __wrap_srand(0); else __real_srand((unsigned)g_time);
+  S = ransacH2el(u, n, px_th * px_th, conf, max_iters, H, mask_out, data_out, 1, 0);
+  for (i = 0; i < 9; ++i) H_out[i] = H[i];
+  if (stats_out) { stats_out[0] = data_out[0]; stats_out[1] = data_out[1]; stats_out[2] = data_out[2]; stats_out[3] = (int)S.I; }
+  free(u);
+  g_mode = 0;
+  return 0;
+}
+int ref_h_from_2el(const double *ua, const double *ub, double *h) {
+  double u[20], N1[9], D1[9], N2[9], D2[9];
+  int samidx[2] = {0, 1};
+  memcpy(u, ua, 80); memcpy(u + 10, ub, 80);
+  getTransf(u, N1, D1); getTransf(u + 10, N2, D2);
+  return A2toRH(N1, D1, N2, D2, u, samidx, h) ? 0 : 1;
+}

@@ -12,6 +12,8 @@ from .utils import (findHomography,
                     findFundamentalMatrix,
                     findHomographyBatch,
                     findFundamentalMatrixBatch,
+                    findHomographyFromEllipses,
+                    laf_to_ellipse_frame,
                     convert_cv2_kpts_to_xyA,
                     error_type_dict_homography,
                     error_type_dict_fundamental)

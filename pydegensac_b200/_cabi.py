@@ -45,6 +45,8 @@ def lib():
         L.dgb200_find_homography_ragged.argtypes = [dp, dp, i32, ci, ci, cd, cd, ci, ci, ci, cd, u64, dp, u8, i32]
         L.dgb200_find_fundamental_ragged_dev.argtypes = [vp, vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, ci, vp, vp, vp, vp, vp]
         L.dgb200_find_homography_ragged_dev.argtypes = [vp, vp, vp, ci, ci, ci, cd, cd, ci, ci, ci, cd, vp, vp, vp, vp, vp]
+        L.dgb200_find_homography_2el_batch.argtypes = [dp, ci, ci, cd, cd, ci, u64, dp, u8, i32]
+        L.dgb200_find_homography_2el_batch_dev.argtypes = [vp, ci, ci, cd, cd, ci, vp, vp, vp, vp, vp]
         L.dgb200_match_workspace_bytes.restype = ctypes.c_size_t
         L.dgb200_match_workspace_bytes.argtypes = [ci, ci]
         L.dgb200_match_descriptors_dev.argtypes = [vp, ci, vp, ci, ci, ctypes.c_float, ci, vp, vp, ci, vp, vp, vp, vp, ci, ci, vp, vp, vp]
@@ -190,6 +192,33 @@ def homography_batch_dev(d_p1, d_p2, P, N, dim, px_th, conf, max_iters, error_ty
     rc = lib().dgb200_find_homography_batch_dev_ex(d_p1, d_p2, P, N, dim, float(px_th), float(conf), int(max_iters),
                                                    int(error_type), int(bool(sym_check)), float(laf_coef), d_seeds, d_H,
                                                    d_mask, d_stats, stream, int(flags))
+    if rc != 0:
+        _raise(rc)
+
+
+def homography_2el_batch(u10, px_th, conf, max_iters, seeds):
+    """ransacH2el over a batch: u10 [P,N,10] rows (x', y', a', b', c', x, y, a, b, c) -> raw H [P,3,3], mask, stats."""
+    u = np.ascontiguousarray(u10, dtype=np.float64)
+    if u.ndim == 2:
+        u = u[None]
+    if u.ndim != 3 or u.shape[2] != 10:
+        raise ValueError("u10 should be an array with dims [n,10] or [P,n,10]")
+    P, N, _ = u.shape
+    H = np.zeros((P, 3, 3), dtype=np.float64)
+    mask = np.zeros((P, N), dtype=np.uint8)
+    stats = np.zeros((P, 4), dtype=np.int32)
+    s = _seeds(seeds, P)
+    rc = lib().dgb200_find_homography_2el_batch(_p(u, ctypes.c_double), P, N, float(px_th), float(conf), int(max_iters),
+                                                _p(s, ctypes.c_uint64) if s is not None else None,
+                                                _p(H, ctypes.c_double), _p(mask, ctypes.c_uint8), _p(stats, ctypes.c_int32))
+    if rc != 0:
+        _raise(rc)
+    return H, mask.view(np.bool_), stats
+
+
+def homography_2el_batch_dev(d_u10, P, N, px_th, conf, max_iters, d_seeds, d_H, d_mask, d_stats, stream=0):
+    rc = lib().dgb200_find_homography_2el_batch_dev(d_u10, P, N, float(px_th), float(conf), int(max_iters), d_seeds, d_H,
+                                                    d_mask, d_stats, stream)
     if rc != 0:
         _raise(rc)
 

@@ -24,6 +24,7 @@
 #include "../../include/degensac_b200.h"
 #include "engine_f.h"
 #include "engine_h.h"
+#include "engine_h2el.h"
 #include "filter32.h"
 #include "workspace.h"
 
@@ -99,7 +100,7 @@ struct BatchArgs {
   long long wait_cycles;   // patience of that wait
 };
 
-template <int KIND>  // 0: fundamental matrix, 1: homography
+template <int KIND>  // 0: fundamental matrix, 1: homography, 2: homography from elliptical features (rows u10, engine_h2el.h)
 __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel(BatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // The CTA hosts blockDim.x / GT groups (one in the default build); each owns one pair at a time, its own scratch,
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
     const int n = a.offsets ? a.offsets[p + 1] - a.offsets[p] : a.n;
     c.N = n;
     const double* g1 = a.x1y1 + row0 * a.dim;
-    const double* g2 = a.x2y2 + row0 * a.dim;
+    const double* g2 = (KIND == 2) ? g1 + 5 : a.x2y2 + row0 * a.dim;   // u10 rows: (x', y', a', b', c', x, y, a, b, c)
     if (a.dim == 2 && a.aligned16) {   // rows are 16 bytes, so every pair of a ragged batch starts aligned too
       const double2* v1 = reinterpret_cast<const double2*>(g1);
       const double2* v2 = reinterpret_cast<const double2*>(g2);
@@ -202,6 +203,11 @@ __global__ void __launch_bounds__(kMaxThreads, DG_LB_BLOCKS) ransac_pairs_kernel
       P.do_sym = P.sym_th > 0; P.seed = seed; P.chunk = a.chunk;
       P.final_lsq = (a.flags & DGB200_FLAG_FINAL_LSQ) ? 1 : 0;
       dg::ransac_F_pair(c, P, W, model, mask, s_stats);
+    } else if (KIND == 2) {
+      c.t32 = nullptr;
+      dg::H2Params P;
+      P.th = a.px_th * a.px_th; P.conf = a.conf; P.max_iters = a.max_iters; P.seed = seed; P.chunk = a.chunk;
+      dg::ransac_H2el_pair(c, P, W, g1, model, mask, s_stats);
     } else {
       c.t32 = nullptr;
       if (a.filter32 && a.metric == dg::H_SAMPSON) {   // FP32 upper-bound filter of the H wave (Sampson metric)
@@ -377,7 +383,7 @@ int launch(const Job& j, cudaStream_t st, const int* d_ready = nullptr, int* d_s
   size_t smem = sc_bytes;
   a.pts_in_smem = 0;
   a.tile32_in_smem = 0;
-  a.filter32 = (env_int("DGB200_FILTER32", 1) != 0 && (KIND == 0 || j.metric == dg::H_SAMPSON)) ? 1 : 0;   // parity switch, read at every launch
+  a.filter32 = (env_int("DGB200_FILTER32", 1) != 0 && (KIND == 0 || (KIND == 1 && j.metric == dg::H_SAMPSON))) ? 1 : 0;   // parity switch, read at every launch
   a.aligned16 = ((((uintptr_t)j.d1) | ((uintptr_t)j.d2)) & 15) == 0 ? 1 : 0;
   if (tile32 && a.filter32 && smem + tile32 <= g_c.smem_optin && env_int("DGB200_TILE32_SMEM", 0) != 0) {
     // DGB200_TILE32_SMEM=1: the tile in shared memory (when DG_LB_BLOCKS CTAs per SM still fit).  Default: in the slab,
@@ -425,6 +431,11 @@ int check_args(int kind, const void* p1, const void* p2, int n_pairs, int n, int
                const void* m, const void* k) {
   if (!p1 || !p2 || !m || !k) return fail(DGB200_E_ARG, "null buffer");
   if (n_pairs < 1) return fail(DGB200_E_ARG, "n_pairs must be >= 1");
+  if (kind == 2) {
+    if (dim != 10) return fail(DGB200_E_ARG, "u10 should be an array with dims [n,10]");
+    if (n < 4) return fail(DGB200_E_ARG, "u10 should be an array with dims [n,10], n>=4");
+    return 0;
+  }
   if (dim != 2 && dim != 6) return fail(DGB200_E_ARG, "x1y1 should be an array with dims [n,2], [n,6]");
   if (kind == 0 && n < 8) return fail(DGB200_E_ARG, "x1y1 should be an array with dims [n,2], n>=8");
   if (kind == 1 && n < 4) return fail(DGB200_E_ARG, "x1y1 should be an array with dims [n,2], n>=4");
@@ -438,7 +449,7 @@ int check_offsets(int kind, const int32_t* offsets, int n_pairs, int* n_max, lon
   if (!offsets) return fail(DGB200_E_ARG, "null offsets");
   if (offsets[0] != 0) return fail(DGB200_E_ARG, "offsets[0] must be 0");
   int mx = 0;
-  const int min_n = kind == 0 ? 8 : 4;
+  const int min_n = kind == 0 ? 8 : 4;   // (kind 2, elliptical features: 4 as well)
   for (int p = 0; p < n_pairs; ++p) {
     const long long n = (long long)offsets[p + 1] - offsets[p];
     if (n < min_n) return fail(DGB200_E_ARG, kind == 0 ? "every pair needs n >= 8 correspondences" : "every pair needs n >= 4 correspondences");
@@ -522,7 +533,8 @@ int run_host(const double* x1y1, const double* x2y2, const int32_t* offsets, int
     const size_t off = row_of(done) * dim;
     const size_t elems = (row_of(done + cnt) - row_of(done)) * dim;
     const cudaError_t e1 = cudaMemcpyAsync(d1 + off, x1y1 + off, sizeof(double) * elems, cudaMemcpyHostToDevice, cs);
-    const cudaError_t e2 = cudaMemcpyAsync(d2 + off, x2y2 + off, sizeof(double) * elems, cudaMemcpyHostToDevice, cs);
+    const cudaError_t e2 = (KIND == 2) ? cudaSuccess   // one array of u10 rows
+                                       : cudaMemcpyAsync(d2 + off, x2y2 + off, sizeof(double) * elems, cudaMemcpyHostToDevice, cs);
     done += cnt;
     g_c.h_ready[ci] = (e1 == cudaSuccess && e2 == cudaSuccess) ? done : n_pairs + 1;   // on a failed copy release the CTAs anyway
     cudaMemcpyAsync(g_c.ready, &g_c.h_ready[ci], sizeof(int), cudaMemcpyHostToDevice, cs);
@@ -688,6 +700,18 @@ int dgb200_find_homography(const double* x1y1, const double* x2y2, int n, int di
                            uint8_t* mask_out, int32_t* stats_out) {
   return run_host<1>(x1y1, x2y2, nullptr, 1, n, dim, px_th, conf, max_iters, error_type, sym_check, laf_coef, 0, &seed,
                      H_out, mask_out, stats_out);
+}
+
+int dgb200_find_homography_2el_batch(const double* u10, int n_pairs, int n, double px_th, double conf, int max_iters,
+                                     const uint64_t* seeds, double* H_out, uint8_t* mask_out, int32_t* stats_out) {
+  return run_host<2>(u10, u10, nullptr, n_pairs, n, 10, px_th, conf, max_iters, 0, 0, 0.0, 0, seeds, H_out, mask_out,
+                     stats_out);
+}
+int dgb200_find_homography_2el_batch_dev(const double* d_u10, int n_pairs, int n, double px_th, double conf,
+                                         int max_iters, const uint64_t* d_seeds, double* d_H_out, uint8_t* d_mask_out,
+                                         int32_t* d_stats_out, void* stream) {
+  return run_dev<2>(d_u10, d_u10, nullptr, n_pairs, n, 10, px_th, conf, max_iters, 0, 0, 0.0, 0, d_seeds, d_H_out,
+                    d_mask_out, d_stats_out, stream);
 }
 
 int dgb200_version(void) { return 2; }

@@ -252,7 +252,13 @@ DG_HDN bool h_from_4pt(const double* px1, const double* py1, const double* px2, 
 // zeroed, so the "null space" is taken of a scrambled matrix (9 of its entries come from uninitialised
 // stack, taken as 0 here).  The outcome is a model without support, i.e. that LO repetition is a no-op;
 // reproducing it keeps the LO trajectory identical to the reference's.
+#ifdef DG_EIG_STATS
+static long g_u2h4_calls = 0;   // (host emulation: lets the tests tell which inputs reach this undefined corner of the reference)
+#endif
 DG_HDN void h_from_4pt_u2h_quirk(const double* px1, const double* py1, const double* px2, const double* py2, double* h) {
+#ifdef DG_EIG_STATS
+  ++g_u2h4_calls;
+#endif
   double Z[81], T[81], sol[81];
   #pragma unroll 1
   for (int i = 0; i < 81; ++i) { Z[i] = 0.0; sol[i] = 0.0; }

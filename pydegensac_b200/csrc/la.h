@@ -12,41 +12,44 @@ namespace dg {
 // column, the k-th null vector is (-column of the reduced matrix ; unit on the free column).
 // Returns the number of null vectors (written to ns[k*9 + ...]).
 // ---------------------------------------------------------------------------------------------
-DG_HDN int nullspace9(double* M, double* ns) {
+template <int NN>
+DG_HD int nullspaceN(double* M, double* ns) {
   const double tol = 1e-12;
-  int freec[9], pivc[9];
+  int freec[NN], pivc[NN];
   int nfree = 0, npiv = 0, row = 0;
-  for (int col = 0; col < 9; ++col) {
+  #pragma unroll 1
+  for (int col = 0; col < NN; ++col) {
     int best = row;
-    double mag = fabs(M[9 * row + col]);
+    double mag = fabs(M[NN * row + col]);
     #pragma unroll 1
-    for (int r = row + 1; r < 9; ++r) {
-      const double t = fabs(M[9 * r + col]);
+    for (int r = row + 1; r < NN; ++r) {
+      const double t = fabs(M[NN * r + col]);
       if (mag < t) { mag = t; best = r; }
     }
     if (mag < tol) {
       freec[nfree++] = col;
       #pragma unroll 1
-      for (int r = row; r < 9; ++r) M[9 * r + col] = 0.0;
+      for (int r = row; r < NN; ++r) M[NN * r + col] = 0.0;
       continue;
     }
     pivc[npiv++] = col;
     if (best != row) {
       #pragma unroll 1
-      for (int c = col; c < 9; ++c) {
-        const double t = M[9 * row + c];
-        M[9 * row + c] = M[9 * best + c];
-        M[9 * best + c] = t;
+      for (int c = col; c < NN; ++c) {
+        const double t = M[NN * row + c];
+        M[NN * row + c] = M[NN * best + c];
+        M[NN * best + c] = t;
       }
     }
-    const double p = M[9 * row + col];
+    const double p = M[NN * row + col];
     #pragma unroll 1
-    for (int c = col; c < 9; ++c) M[9 * row + c] /= p;
-    for (int r = 0; r < 9; ++r) {
+    for (int c = col; c < NN; ++c) M[NN * row + c] /= p;
+    #pragma unroll 1
+    for (int r = 0; r < NN; ++r) {
       if (r == row) continue;
-      const double a = M[9 * r + col];
+      const double a = M[NN * r + col];
       #pragma unroll 1
-      for (int c = col; c < 9; ++c) M[9 * r + c] -= a * M[9 * row + c];
+      for (int c = col; c < NN; ++c) M[NN * r + c] -= a * M[NN * row + c];
     }
     ++row;
   }
@@ -54,12 +57,14 @@ DG_HDN int nullspace9(double* M, double* ns) {
   for (int k = 0; k < nfree; ++k) {
     const int j = freec[k];
     #pragma unroll 1
-    for (int l = 0; l < npiv; ++l) ns[k * 9 + pivc[l]] = -M[l * 9 + j];
+    for (int l = 0; l < npiv; ++l) ns[k * NN + pivc[l]] = -M[l * NN + j];
     #pragma unroll 1
-    for (int l = 0; l < nfree; ++l) ns[k * 9 + freec[l]] = (j == freec[l]) ? 1.0 : 0.0;
+    for (int l = 0; l < nfree; ++l) ns[k * NN + freec[l]] = (j == freec[l]) ? 1.0 : 0.0;
   }
   return nfree;
 }
+DG_HDN int nullspace9(double* M, double* ns) { return nullspaceN<9>(M, ns); }
+DG_HDN int nullspace15(double* M, double* ns) { return nullspaceN<15>(M, ns); }   // two-ellipse H solver (h2el.h)
 
 // ---------------------------------------------------------------------------------------------
 // Symmetric 9x9 eigen-decomposition by cyclic Jacobi rotations (replaces LAPACK dsyev_, which the

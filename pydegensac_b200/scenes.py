@@ -94,3 +94,43 @@ def scene_H_laf(n=800, n_in=400, seed=0, jitter=0.6):
     A2 = A1 + rng.normal(0, jitter, (n, 4))
     A2[~gt] = rng.normal(0, 6, ((~gt).sum(), 4))
     return np.hstack([p1, A1]), np.hstack([p2, A2]), gt
+
+
+# ---- correspondences of local elliptical features under a planted homography (ransacH2el tests).  Rows u10 =
+# (x', y', a', b', c', x, y, a, b, c) as ranH2el.h:4 documents: image 1 first; each frame the lower-triangular
+# affinity [a 0; b c] at (x, y).
+
+
+def _lower(A):
+    """A R = L with R a rotation and L lower triangular with positive diagonal (same ellipse A * unit circle)."""
+    q, r = np.linalg.qr(A.T)       # A.T = q r  ->  A = r.T q.T
+    L = r.T
+    s = np.sign(np.diag(L)); s[s == 0] = 1
+    return L * s[None, :]
+
+
+def scene_H2el(n, inlier_frac, seed, noise=0.3, size=800.0, frame_noise=0.01):
+    rng = np.random.RandomState(seed)
+    H = np.eye(3) + rng.uniform(-0.15, 0.15, (3, 3)) * np.array([[1, 1, 100], [1, 1, 100], [2e-4, 2e-4, 0]])
+    H[2, 2] = 1.0
+    u = np.zeros((n, 10))
+    n_in = int(round(n * inlier_frac))
+    for i in range(n):
+        x, y = rng.uniform(50, size - 50, 2)
+        A = _lower(np.array([[rng.uniform(5, 20), 0], [rng.uniform(-5, 5), rng.uniform(5, 20)]]))
+        if i < n_in:
+            w = H @ np.array([x, y, 1.0])
+            xp, yp = w[0] / w[2], w[1] / w[2]
+            # Jacobian of the projective map at (x, y)
+            J = (H[:2, :2] - np.outer([xp, yp], H[2, :2])) / w[2]
+            Ap = _lower(J @ A)
+            if noise > 0:
+                xp += rng.normal(0, noise); yp += rng.normal(0, noise)
+            Ap = _lower(Ap * (1 + rng.normal(0, frame_noise, (2, 2)))) if frame_noise > 0 else Ap
+        else:
+            xp, yp = rng.uniform(50, size - 50, 2)
+            Ap = _lower(np.array([[rng.uniform(5, 20), 0], [rng.uniform(-5, 5), rng.uniform(5, 20)]]))
+        u[i] = [xp, yp, Ap[0, 0], Ap[1, 0], Ap[1, 1], x, y, A[0, 0], A[1, 0], A[1, 1]]
+    perm = rng.permutation(n)
+    truth = np.zeros(n, dtype=bool); truth[:n_in] = True
+    return u[perm], truth[perm], H

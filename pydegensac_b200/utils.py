@@ -236,3 +236,49 @@ def findHomographyBatch(pts1, pts2, px_th=1.0, conf=0.999, max_iters=50000, erro
         if np.abs(Hraw[i]).sum() != 0:
             H[i] = np.linalg.inv(Hraw[i].T)
     return (H, mask, stats) if return_stats else (H, mask)
+
+
+def laf_to_ellipse_frame(xyA):
+    """[N,6] rows (x, y, a11, a12, a21, a22) (convert_cv2_kpts_to_xyA) -> [N,5] rows (x, y, a, b, c): the SAME ellipse
+    A * unit-circle written as the lower-triangular frame [a 0; b c] with a, c > 0 that ransacH2el takes (ranH2el.h:4,
+    getTransf ranH2el.c:211-231).  A = L Q with Q a rotation: L L^T = A A^T (Cholesky)."""
+    k = np.asarray(xyA, dtype=np.float64)
+    if k.ndim != 2 or k.shape[1] != 6:
+        raise ValueError("expected [N,6] rows (x, y, a11, a12, a21, a22)")
+    a11, a12, a21, a22 = k[:, 2], k[:, 3], k[:, 4], k[:, 5]
+    s11 = a11 * a11 + a12 * a12
+    s21 = a21 * a11 + a22 * a12
+    s22 = a21 * a21 + a22 * a22
+    a = np.sqrt(s11)
+    b = s21 / a
+    c = np.sqrt(np.maximum(s22 - b * b, 0.0))
+    return np.stack([k[:, 0], k[:, 1], a, b, c], axis=1)
+
+
+def findHomographyFromEllipses(frames1, frames2, px_th=1.0, conf=0.999, max_iters=50000, seed=None, seeds=None,
+                               return_stats=False):
+    """Homography from correspondences of local elliptical features, two correspondences per sample: the reference
+    core's ransacH2el (ranH2el.c:19), which the reference never bound to Python.
+    frames1, frames2: [N,5] (or [P,N,5]) rows (x, y, a, b, c) -- centre and lower-triangular frame [a 0; b c] of the
+    feature in image 1 / image 2 (`laf_to_ellipse_frame` converts [N,6] keypoints).  px_th bounds the Sampson error of
+    the centres (th = px_th^2).  Returns (H, mask) in the findHomography convention: H maps image 1 -> image 2."""
+    from . import _cabi
+    f1 = np.asarray(frames1, dtype=np.float64)
+    f2 = np.asarray(frames2, dtype=np.float64)
+    if f1.shape != f2.shape or f1.ndim not in (2, 3) or f1.shape[-1] != 5:
+        raise ValueError("frames1, frames2 should be arrays with dims [n,5] (x, y, a, b, c)")
+    single = f1.ndim == 2
+    if single:
+        f1, f2 = f1[None], f2[None]
+    P = f1.shape[0]
+    if seeds is None:
+        seeds = np.full(P, _seed_value(seed), dtype=np.uint64) if single else _batch_seeds(None, P)
+    u10 = np.concatenate([f1, f2], axis=2)
+    Hraw, mask, stats = _cabi.homography_2el_batch(u10, px_th, conf, max_iters, seeds)
+    H = np.zeros_like(Hraw)
+    for i in range(P):
+        if np.abs(Hraw[i]).sum() != 0:
+            H[i] = np.linalg.inv(Hraw[i].T)
+    if single:
+        H, mask, stats = H[0], mask[0], stats[0]
+    return (H, mask, stats) if return_stats else (H, mask)

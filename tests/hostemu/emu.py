@@ -53,3 +53,30 @@ def find_homography_raw(p1, p2, px_th=1.0, conf=0.999, max_iters=50000, error_ty
                                    stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
     assert rc == 0, rc
     return H.reshape(3, 3), mask.astype(bool), stats
+
+
+def find_homography_2el_raw(u10, px_th=1.0, conf=0.999, max_iters=50000, seed=0, chunk=512):
+    u = np.ascontiguousarray(u10, dtype=np.float64)
+    n = u.shape[0]
+    H = np.zeros(9); mask = np.zeros(n, dtype=np.uint8); stats = np.zeros(4, dtype=np.int32)
+    rc = lib().emu_find_homography_2el(_dp(u), n, ctypes.c_double(px_th), ctypes.c_double(conf), int(max_iters),
+                                       ctypes.c_uint64(seed), int(chunk), _dp(H),
+                                       mask.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
+                                       stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert rc == 0, rc
+    return H.reshape(3, 3), mask.astype(bool), stats
+
+
+def h_from_2el(ua, ub):
+    ua = np.ascontiguousarray(ua, dtype=np.float64); ub = np.ascontiguousarray(ub, dtype=np.float64)
+    h = np.zeros(9)
+    ok = lib().emu_h_from_2el(_dp(ua), _dp(ub), _dp(h))
+    return bool(ok), h
+
+
+def u2h4_calls(reset=True):
+    """How often the fit took the reference's len == 4 branch of u2h (Htools.c:108-116), whose outcome depends on nine
+    uninitialised stack doubles in the reference."""
+    f = lib().emu_u2h4_calls
+    f.restype = ctypes.c_long
+    return int(f(int(reset)))

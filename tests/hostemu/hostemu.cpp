@@ -9,6 +9,7 @@
 #define DG_EIG_STATS 1
 #include "../../pydegensac_b200/csrc/engine_f.h"
 #include "../../pydegensac_b200/csrc/engine_h.h"
+#include "../../pydegensac_b200/csrc/engine_h2el.h"
 #include "../../pydegensac_b200/csrc/workspace.h"
 
 using namespace dg;
@@ -96,6 +97,20 @@ extern "C" int emu_find_homography(const double* x1y1, const double* x2y2, int n
   free(E.slab); free(E.tile);
   return 0;
 }
+
+extern "C" int emu_find_homography_2el(const double* u10, int n, double px_th, double conf, int max_iters, uint64_t seed,
+                                       int chunk, double* H, unsigned char* mask, int* stats) {
+  if (n < 4) return -1;
+  Emu E;
+  emu_setup(E, u10, u10 + 5, n, 10, chunk);
+  H2Params P;
+  P.th = px_th * px_th; P.conf = conf; P.max_iters = max_iters; P.seed = seed; P.chunk = chunk;
+  ransac_H2el_pair(E.c, P, E.W, u10, H, mask, stats);
+  free(E.slab); free(E.tile);
+  return 0;
+}
+extern "C" long emu_u2h4_calls(int reset) { const long v = g_u2h4_calls; if (reset) g_u2h4_calls = 0; return v; }
+extern "C" int emu_h_from_2el(const double* ua, const double* ub, double* h) { return h_from_2el(ua, ub, h) ? 1 : 0; }
 
 // ---- leaf exports for known-answer tests against the reference's own leaves ----
 extern "C" int emu_nullspace9(double* M, double* ns) { return nullspace9(M, ns); }
