@@ -33,6 +33,8 @@ struct BlockScratch {
   int counter[4];                  // atomic counters of the hypothesis wave
   int pair, ok;                    // the group's current image pair / "its input has landed" flag
   int stats[4];
+  int fh_cnt[16];                  // blk_inner_FH: support of the fifteen repetitions' models ...
+  double fh_F[15 * 9];             // ... and the models
   WarpScratch ws[1];               // warp 0's tile for the cooperative 9x9 / 8x9 solves
   union {                          // never live at the same time:
     WarpScratch wsx[kGroupWarpsScratch >= 5 ? 4 : 1];   //   tiles of warps 1..4 (the five checksample triplets run side by side)

@@ -416,6 +416,74 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
   #pragma unroll 1
   for (int i = c.tid; i < c.N; i += c.nt) inl[i] = 0;
   DG_SYNC();
+#if DG_DEVICE_PASS
+  // The fifteen repetitions are INDEPENDENT up to the bookkeeping: every one consumes exactly ten draws and fits its own
+  // 6 + 4 sample; only "best so far" (max_i, max_s) and the rare u2Fit are order-dependent.  So the samples, the ten-point
+  // fits (one warp each, five side by side -- the tiles of the checksample triplets) and the support counts (one warp
+  // per model) are computed up front, and the reference's loop is then replayed in order on the stored (model, count)
+  // pairs; a full residual row is produced only for the repetitions that improve on the best (a handful of fifteen).
+  {
+    double* fhF = c.sc->fh_F;
+    int* fhC = c.sc->fh_cnt;
+    const int nfit = (kGroupWarpsScratch >= 5 && c.nw >= 5) ? 5 : 1;   // warp tiles available side by side
+    #pragma unroll 1
+    for (int base = 0; base < 15; base += nfit) {
+      DG_SYNC();
+      if (c.wid < nfit) {
+        const int rep = base + c.wid;
+        WarpScratch* ws = c.sc->warp_tile(c.wid);
+        int* usam_w = reinterpret_cast<int*>(ws->V);
+        warp_dual_sample(uH, nH, uO, nO, usam_w, cur.seed, cur.k, cur.j + 10u * (uint32_t)rep, c.lane);
+        __syncwarp();
+        warp_fit_F_small(c, ws, ws->aux, usam_w, 10, nullptr, fhF + 9 * rep);
+      }
+    }
+    DG_SYNC();
+    #pragma unroll 1
+    for (int rep = c.wid; rep < 15; rep += c.nw) {
+      double aF[9];
+      for (int i = 0; i < 9; ++i) aF[i] = fhF[9 * rep + i];
+      int cnt = 0;
+      #pragma unroll 1
+      for (int i = c.lane; i < c.N; i += 32)
+        cnt += (f_resid(F_SAMPSON, aF, ld_soa(c.x1 + i), ld_soa(c.y1 + i), ld_soa(c.x2 + i), ld_soa(c.y2 + i)) < th) ? 1 : 0;
+      cnt = warp_sum_i(cnt);
+      if (c.lane == 0) fhC[rep] = cnt;
+    }
+    DG_SYNC();
+    cur.j += 150;
+    #pragma unroll 1
+    for (unsigned rep = 0; rep < 15; ++rep) {
+      unsigned no_i = (unsigned)fhC[rep];
+      if (!(max_i < no_i) && !(no_i > max_s)) continue;
+      double aF[9];
+      for (int i = 0; i < 9; ++i) aF[i] = fhF[9 * rep + i];
+      blk_resid_F(c, F_SAMPSON, aF, Ds);
+      #pragma unroll 1
+      for (int i = c.tid; i < c.N; i += c.nt) v[i] = (Ds[i] < th) ? 1 : 0;
+      DG_SYNC();
+      if (max_i < no_i) {
+        #pragma unroll 1
+        for (int i = c.tid; i < c.N; i += c.nt) inl[i] = v[i];
+        for (int i = 0; i < 9; ++i) F[i] = aF[i];
+        max_i = no_i;
+        DG_SYNC();
+      }
+      if (no_i > max_s) {
+        max_s = no_i;
+        DG_PROF_COUNT(38, 1);
+        { DG_PROF_BEGIN(37); no_i = blk_u2Fit(c, W, aF, v, th, th * 3, 4); DG_PROF_END(37); }
+        if (max_i < no_i) {
+          #pragma unroll 1
+          for (int i = c.tid; i < c.N; i += c.nt) inl[i] = v[i];
+          for (int i = 0; i < 9; ++i) F[i] = aF[i];
+          max_i = no_i;
+          DG_SYNC();
+        }
+      }
+    }
+  }
+#else
   #pragma unroll 1
   for (unsigned rep = 0; rep < 15; ++rep) {
     // dual_sample: fresh identity permutations, `pos <-> rand()%len` swaps (DegUtils.c:596-632)
@@ -491,6 +559,7 @@ DG_ENGN void blk_inner_FH(const Ctx& c, Workspace& W, const int* uH, int nH, con
       }
     }
   }
+#endif
 }
 
 // F = transpose( [e]x * H^T ) for the epipole e through two off-plane correspondences

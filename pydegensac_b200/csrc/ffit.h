@@ -191,6 +191,74 @@ DG_ENGN void blk_randsubset(const Ctx& c, int* list, int max_sz, int siz, DrawCu
   DG_PROF_END(23);
 }
 
+// Warp-level F fit on a SMALL support (8 < len <= 32): Hartley normalisation, 9 x 9 normal matrix, smallest
+// eigenvector, rank 2, de-normalisation -- all inside the calling warp (one lane per correspondence).  `ws`: the warp's
+// own tile; `rows`: 9 * len doubles of scratch (may alias ws->aux: dead before the eigen-solver starts); lane 0 writes
+// the model to out[0..8].  Called by warp 0 for the block (blk_fit_F) and by several warps side by side where the
+// reference's repetitions are independent (blk_inner_FH).
+DG_ENGN void warp_fit_F_small(const Ctx& c, WarpScratch* ws, double* rows, const int* idx, int len, const double* w,
+                              double* out) {
+  const int W = DG_DEVICE_PASS ? 32 : 1;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  #pragma unroll 1
+  for (int j = c.lane; j < len; j += W) {
+    const int p = idx[j];
+    s0 += c.x1[p]; s1 += c.y1[p]; s2 += c.x2[p]; s3 += c.y2[p];
+  }
+  s0 = wl_sum(s0); s1 = wl_sum(s1); s2 = wl_sum(s2); s3 = wl_sum(s3);
+  double A1[3], A2[3];
+  A1[1] = s0 / len; A1[2] = s1 / len; A2[1] = s2 / len; A2[2] = s3 / len;
+  double d1 = 0.0, d2 = 0.0;
+  #pragma unroll 1
+  for (int j = c.lane; j < len; j += W) {
+    const int p = idx[j];
+    double a = c.x1[p] - A1[1], b = c.y1[p] - A1[2];
+    d1 += sqrt(a * a + b * b);
+    a = c.x2[p] - A2[1]; b = c.y2[p] - A2[2];
+    d2 += sqrt(a * a + b * b);
+  }
+  A1[0] = wl_sum(d1); A2[0] = wl_sum(d2);
+  if (A1[0] != 0) A1[0] = len * sqrt(2.0) / A1[0];
+  if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
+  A1[1] *= -A1[0]; A1[2] *= -A1[0];
+  A2[1] *= -A2[0]; A2[2] *= -A2[0];
+  #pragma unroll 1
+  for (int j = c.lane; j < len; j += W) {
+    const int p = idx[j];
+    double a[3], b[3];
+    a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
+    b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
+    const double ww = w ? w[p] : 1.0;
+    for (int k = 0; k < 3; ++k)
+      for (int l = 0; l < 3; ++l) {
+        double v = a[l] * b[k];
+        if (w) v *= ww;
+        rows[9 * j + 3 * k + l] = v;
+      }
+  }
+  DG_WSYNC();
+  #pragma unroll 1
+  for (int t = c.lane; t < 45; t += W) {
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    const int jj = t - i * (i + 1) / 2;
+    double s = 0.0;
+    #pragma unroll 1
+    for (int r = 0; r < len; ++r) s += rows[9 * r + i] * rows[9 * r + jj];
+    ws->A[9 * i + jj] = s;
+    ws->A[9 * jj + i] = s;
+  }
+  DG_WSYNC();
+  { DG_PROF_BEGIN(29); warp_smallest_eigvec9(ws, c.lane, W); DG_PROF_END(29); }
+  if (c.lane == 0) {
+    double q[9];
+    for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
+    { DG_PROF_BEGIN(24); enforce_rank2(q); DG_PROF_END(24); }
+    denorm_F(q, A1, A2);
+    for (int i = 0; i < 9; ++i) out[i] = q[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // F from a list of correspondences: reference u2f / u2fw (Ftools.c:350-458).
 //   len > 8 : Hartley normalisation -> 9x9 normal matrix (block reduction) -> smallest eigenvector
@@ -248,69 +316,7 @@ DG_ENGN void blk_fit_F(const Ctx& c, const int* idx, int len, const double* w, d
     // Small support (the 9..14-point inner LO samples, 10-point plane+parallax samples): the whole fit runs
     // inside warp 0 -- one lane per correspondence, no block-wide reduction, rows kept in shared memory.
     DG_SYNC();
-    if (c.wid == 0) {
-      const int W = DG_DEVICE_PASS ? 32 : 1;
-      WarpScratch* ws = &c.sc->ws[0];
-      double* rows = c.sc->vec;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      #pragma unroll 1
-      for (int j = c.lane; j < len; j += W) {
-        const int p = idx[j];
-        s0 += c.x1[p]; s1 += c.y1[p]; s2 += c.x2[p]; s3 += c.y2[p];
-      }
-      s0 = wl_sum(s0); s1 = wl_sum(s1); s2 = wl_sum(s2); s3 = wl_sum(s3);
-      double A1[3], A2[3];
-      A1[1] = s0 / len; A1[2] = s1 / len; A2[1] = s2 / len; A2[2] = s3 / len;
-      double d1 = 0.0, d2 = 0.0;
-      #pragma unroll 1
-      for (int j = c.lane; j < len; j += W) {
-        const int p = idx[j];
-        double a = c.x1[p] - A1[1], b = c.y1[p] - A1[2];
-        d1 += sqrt(a * a + b * b);
-        a = c.x2[p] - A2[1]; b = c.y2[p] - A2[2];
-        d2 += sqrt(a * a + b * b);
-      }
-      A1[0] = wl_sum(d1); A2[0] = wl_sum(d2);
-      if (A1[0] != 0) A1[0] = len * sqrt(2.0) / A1[0];
-      if (A2[0] != 0) A2[0] = len * sqrt(2.0) / A2[0];
-      A1[1] *= -A1[0]; A1[2] *= -A1[0];
-      A2[1] *= -A2[0]; A2[2] *= -A2[0];
-      #pragma unroll 1
-      for (int j = c.lane; j < len; j += W) {
-        const int p = idx[j];
-        double a[3], b[3];
-        a[0] = c.x1[p] * A1[0] + A1[1]; a[1] = c.y1[p] * A1[0] + A1[2]; a[2] = 1.0;
-        b[0] = c.x2[p] * A2[0] + A2[1]; b[1] = c.y2[p] * A2[0] + A2[2]; b[2] = 1.0;
-        const double ww = w ? w[p] : 1.0;
-        for (int k = 0; k < 3; ++k)
-          for (int l = 0; l < 3; ++l) {
-            double v = a[l] * b[k];
-            if (w) v *= ww;
-            rows[9 * j + 3 * k + l] = v;
-          }
-      }
-      DG_WSYNC();
-      #pragma unroll 1
-      for (int t = c.lane; t < 45; t += W) {
-        int i = 0;
-        while ((i + 1) * (i + 2) / 2 <= t) ++i;
-        const int jj = t - i * (i + 1) / 2;
-        double s = 0.0;
-        #pragma unroll 1
-        for (int r = 0; r < len; ++r) s += rows[9 * r + i] * rows[9 * r + jj];
-        ws->A[9 * i + jj] = s;
-        ws->A[9 * jj + i] = s;
-      }
-      DG_WSYNC();
-      { DG_PROF_BEGIN(29); warp_smallest_eigvec9(ws, c.lane, W); DG_PROF_END(29); }
-      if (c.lane == 0) {
-        double q[9];
-        for (int i = 0; i < 9; ++i) q[i] = ws->cs[i];
-        { DG_PROF_BEGIN(24); enforce_rank2(q); DG_PROF_END(24); }
-        denorm_F(q, A1, A2);
-        for (int i = 0; i < 9; ++i) c.sc->bc[i] = q[i];
-      }
-    }
+    if (c.wid == 0) warp_fit_F_small(c, &c.sc->ws[0], c.sc->vec, idx, len, w, c.sc->bc);
     bc_fetch(c, f, 9);
     DG_PROF_END(8);
     return;

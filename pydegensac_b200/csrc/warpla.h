@@ -276,6 +276,133 @@ __device__ __noinline__ bool warp_smallest_eigvec9_reg(WarpScratch* ws, int lane
 }
 
 // ---------------------------------------------------------------------------------------------
+// Inverse iteration on the EXPLICIT inverse.  One warp runs the eigen-solver while the rest of the CTA waits, and a
+// lone warp is paid in dependent-instruction latency (~8 cycles per instruction): the substitution version above spends
+// 16 shuffle + FMA steps and three butterflies per solve, ~4 000 dynamic instructions and 25-29 k cycles per call in situ
+// (tools/prof_phases.py).  Here the factorisation is followed by nine column solves run side by side -- lane i solves
+// L D L^T z = e_i entirely in its own registers (the factor is broadcast from shared memory) and keeps z = row i of
+// M = (A - sigma I)^-1 -- after which one inverse-iteration step is a single matrix-vector product: nine independent
+// shuffles and nine FMAs per lane instead of two sequential triangular sweeps.  Same start vector (M e_8 is parallel to
+// L^-T e_8), same convergence rule, same Rayleigh-shift refactorisation for clustered small eigenvalues, and the same
+// final test of |A x - rho x| against the ORIGINAL matrix, so a wrong answer cannot get out: failure sends the caller
+// to the substitution version / Jacobi.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool eig9_inverse_rows(const double* A, int r, int lane, bool act, double sigma, double tiny,
+                                                  double* T, double* Dv, double (&m)[9]) {
+  double a[9];
+  a[0] = A[r * 9 + 0] - ((lane == 0) ? sigma : 0.0); a[1] = A[r * 9 + 1] - ((lane == 1) ? sigma : 0.0);
+  a[2] = A[r * 9 + 2] - ((lane == 2) ? sigma : 0.0); a[3] = A[r * 9 + 3] - ((lane == 3) ? sigma : 0.0);
+  a[4] = A[r * 9 + 4] - ((lane == 4) ? sigma : 0.0); a[5] = A[r * 9 + 5] - ((lane == 5) ? sigma : 0.0);
+  a[6] = A[r * 9 + 6] - ((lane == 6) ? sigma : 0.0); a[7] = A[r * 9 + 7] - ((lane == 7) ? sigma : 0.0);
+  a[8] = A[r * 9 + 8] - ((lane == 8) ? sigma : 0.0);
+  bool neg = false;
+  double dsel = 1.0;
+  eig9_factor_step<0>(a, lane, tiny, neg, dsel); eig9_factor_step<1>(a, lane, tiny, neg, dsel);
+  eig9_factor_step<2>(a, lane, tiny, neg, dsel); eig9_factor_step<3>(a, lane, tiny, neg, dsel);
+  eig9_factor_step<4>(a, lane, tiny, neg, dsel); eig9_factor_step<5>(a, lane, tiny, neg, dsel);
+  eig9_factor_step<6>(a, lane, tiny, neg, dsel); eig9_factor_step<7>(a, lane, tiny, neg, dsel);
+  eig9_factor_step<8>(a, lane, tiny, neg, dsel);
+  __syncwarp();
+  if (act) {
+    double* t = T + lane * 9;     // row i: L[i][k] for k < i
+    t[0] = a[0]; t[1] = a[1]; t[2] = a[2]; t[3] = a[3]; t[4] = a[4]; t[5] = a[5]; t[6] = a[6]; t[7] = a[7]; t[8] = a[8];
+    Dv[lane] = 1.0 / dsel;
+  }
+  __syncwarp();
+  // column r of the inverse: forward sweep (unit lower factor), diagonal, backward sweep (transposed factor); every index
+  // into m[] is a literal, every factor entry one broadcast shared-memory load
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m[i] = (r == i) ? 1.0 : 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int i = k + 1; i < 9; ++i) m[i] = fma(-T[i * 9 + k], m[k], m[i]);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m[i] *= Dv[i];
+#pragma unroll
+  for (int k = 8; k > 0; --k)
+#pragma unroll
+    for (int i = 0; i < k; ++i) m[i] = fma(-T[k * 9 + i], m[k], m[i]);
+  return neg;
+}
+
+__device__ __noinline__ bool warp_smallest_eigvec9_inv(WarpScratch* ws, int lane) {
+  const bool act = lane < 9;
+  const int r = act ? lane : 0;            // idle lanes shadow row 0 (their values are never read)
+  const double* A = ws->A;
+  double* T = ws->aux;
+  double* Dv = ws->aux + 81;
+  double fro = 0.0;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) { const double v = A[r * 9 + j]; fro += v * v; }
+  fro = wl_sum(act ? fro : 0.0);
+  if (!((fro > 0.0) && (fro < 1e300))) return false;
+  const double tiny = sqrt(fro) * 1e-30;
+  double m[9], x = 0.0;
+  double sigma = 0.0, good = 0.0;
+  bool need = true, have_x = false, done = false;
+  int nfac = 0, allow_at = 1;
+#pragma unroll 1
+  for (int it = 0; it < 16 && !done; ++it) {
+#pragma unroll 1
+    while (need) {
+      const bool neg = eig9_inverse_rows(A, r, lane, act, sigma, tiny, T, Dv, m);
+      ++nfac;
+      if (sigma > good && neg) { sigma = good; allow_at = it + 2; continue; }   // overshoot: back to the last good shift
+      good = sigma;
+      need = false;
+    }
+    if (!have_x) {                           // x = M e_8 (parallel to L^-T e_8), normalised
+      double y = act ? m[8] : 0.0;
+      const double n2 = wl_sum(y * y);
+      if (!(n2 > 0.0) || !(n2 < 1e300)) return false;
+      x = y * rsqrt(n2);
+      have_x = true;
+    }
+    double y0 = m[0] * shfl_d(x, 0), y1 = m[1] * shfl_d(x, 1), y2 = m[2] * shfl_d(x, 2);
+    y0 = fma(m[3], shfl_d(x, 3), y0); y1 = fma(m[4], shfl_d(x, 4), y1); y2 = fma(m[5], shfl_d(x, 5), y2);
+    y0 = fma(m[6], shfl_d(x, 6), y0); y1 = fma(m[7], shfl_d(x, 7), y1); y2 = fma(m[8], shfl_d(x, 8), y2);
+    double y = (y0 + y1) + y2;
+    if (!act) y = 0.0;
+    double n2 = y * y, dot = y * x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    if (!(n2 > 0.0) || !(n2 < 1e300)) return false;
+    const double xn = y * ((dot < 0.0 ? -1.0 : 1.0) * rsqrt(n2));
+    const double df = xn - x;
+    x = xn;
+    const double ch = wl_sum(df * df);
+    if (ch < 1e-28) { done = true; break; }
+    if (it >= allow_at && ch > 1e-10 && nfac < 8) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) s = fma(A[r * 9 + j], shfl_d(x, j), s);
+      if (!act) s = 0.0;
+      const double rho = wl_sum(s * x);
+      const double rr = s - rho * x;
+      const double shift = rho - sqrt(wl_sum(rr * rr));
+      if (shift > sigma) { sigma = shift; need = true; }
+    }
+  }
+  if (!done) return false;
+  // Rayleigh residual against the ORIGINAL matrix
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) s = fma(A[r * 9 + j], shfl_d(x, j), s);
+  if (!act) s = 0.0;
+  const double rho = wl_sum(s * x);
+  const double rr = s - rho * x;
+  const double r2 = wl_sum(rr * rr);
+  if (!(r2 <= 1e-28 * fro)) return false;
+  if (act) ws->cs[lane] = x;
+  __syncwarp();
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Device flavour of warp_null_8x9: lane l keeps row (l & 7) of the 8 x 9 system in registers (four redundant
 // copies across the warp, so xor-shuffles over 4,2,1 leave every lane with the pivot choice), Gauss-Jordan with
 // partial pivoting by ROLE instead of row swaps: the pivot row of column c stays where it is and is marked used.
@@ -358,6 +485,9 @@ DG_ENGN void warp_smallest_eigvec9(WarpScratch* ws, int lane, int W) {
   if (const char* dump = getenv("DG_EIG_DUMP")) { FILE* fp = fopen(dump, "ab"); if (fp) { fwrite(ws->A, sizeof(double), 81, fp); fclose(fp); } }
 #endif
 #if DG_DEVICE_PASS
+#ifndef DG_EIG_SUBST
+  if (warp_smallest_eigvec9_inv(ws, lane)) return;
+#endif
   if (warp_smallest_eigvec9_reg(ws, lane)) return;
   {
     warp_jacobi_eig9(ws, lane, W);
