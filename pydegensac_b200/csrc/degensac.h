@@ -17,8 +17,13 @@
 #include "block.h"
 #include "ffit.h"
 #include "hfit.h"
+#include "filter32.h"
 
 namespace dg {
+
+#ifdef DG_FILTER_CHECK
+static long g_pp_checked = 0, g_pp_violations = 0, g_pp_settled = 0;   // plane-and-parallax count bound (host emulation)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Homography compatible with F through 3 correspondences (Hartley & Zisserman p.318; reference Hdetect,
@@ -611,20 +616,41 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
   if (nN < 4 || nH < 6) return 0;
   #pragma unroll 1
   for (int i = c.tid; i < nN; i += c.nt) ptr[i] = i;
+#if DG_DEVICE_PASS
+  // FP32 tile of the OFF-PLANE correspondences only, in list order, pair-interleaved like the main tile (filter32.h);
+  // lives in the first two residual rows of the plane LO, which are dead here (16 (nN + 1) <= 16 N bytes, nN <= N - 6)
+  float* tileN = reinterpret_cast<float*>(W.dtmp[0]);
+  if (c.t32) {
+    const float* tf = reinterpret_cast<const float*>(c.t32->pts);
+    #pragma unroll 1
+    for (int i = c.tid; i < nN; i += c.nt) {
+      const int p = uN[i];
+      const float* src = tf + 8 * (p >> 1) + (p & 1);
+      float* dst = tileN + 8 * (i >> 1) + (i & 1);
+      dst[0] = src[0]; dst[2] = src[2]; dst[4] = src[4]; dst[6] = src[6];
+      if (i == nN - 1 && !(i & 1)) { dst[1] = 0.f; dst[3] = 0.f; dst[5] = 0.f; dst[7] = 0.f; }
+    }
+  }
+#endif
   DG_SYNC();
   const double th2 = th * 2;
   const int WAVE = c.nw * 8;
   int* pairs = W.itmp[2] + 16;   // WAVE x 2 sampled positions
   int* counts = W.itmp[2] + 16 + 2 * 128;
   int* idxs = reinterpret_cast<int*>(c.sc->vec);   // 2 x 128 swap partners of the current wave (block scratch is idle here)
+  int* vals = idxs + 256;                          // permutation entries they address, as they were before the wave
+  int* wrote = idxs + 512;                         // value each access stores
+  int* prevq = idxs + 768;                         // latest earlier access of the wave to the same entry (-1: none)
   unsigned no_sam = 1;
   while (no_sam < 2 * max_sam) {
     int nw = (int)(2 * max_sam - no_sam);
     if (nw > WAVE) nw = WAVE;
     if (nw > 128) nw = 128;
-    // All threads: the 2*nw draws of the speculative iterations (swap partners) go to shared memory, and the
-    // entries of the persistent permutation they address are pulled towards L1.  Thread 0 then replays the swaps
-    // in order with ptr[0], ptr[1] held in registers.
+    // All threads: the 2*nw draws of the speculative iterations (swap partners) go to shared memory together with the
+    // permutation entries they address (one round of independent loads) and, per access, the latest EARLIER access of
+    // this wave to the same entry.  Thread 0 then replays the swaps in order on shared memory only -- ptr[0], ptr[1] in
+    // registers, an entry touched twice read from the log -- and nothing is written to the permutation until the
+    // outcome of the wave is known (no rewind; the serial chain no longer waits on global memory).
     DG_PROF_BEGIN(32);
     DG_SYNC();
     #pragma unroll 1
@@ -632,32 +658,45 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
       const int pos = q & 1;
       const int idx = pos + 1 + (int)(value31(cur.seed, cur.k, cur.j + (uint32_t)q) % (uint32_t)(nN - pos - 1));
       idxs[q] = idx;
-#if DG_DEVICE_PASS
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr + idx));
-#endif
+      vals[q] = ptr[idx];
     }
     DG_SYNC();
+    #pragma unroll 1
+    for (int q = c.tid; q < 2 * nw; q += c.nt) {
+      const int idx = idxs[q];
+      int pr = -1;
+      if (idx != 1) {
+        #pragma unroll 4
+        for (int t = q - 1; t >= 0; --t)
+          if (idxs[t] == idx) { pr = t; break; }
+      }
+      prevq[q] = pr;
+    }
+    DG_SYNC();
+    DG_PROF_BEGIN(47);
     if (c.tid == 0) {
       int p0 = ptr[0], p1 = ptr[1];
       #pragma unroll 1
       for (int s = 0; s < nw; ++s) {
-        const int i0 = idxs[2 * s], i1 = idxs[2 * s + 1];
+        const int q0 = 2 * s, q1 = 2 * s + 1;
         int v;
-        if (i0 == 1) { v = p1; p1 = p0; } else { v = ptr[i0]; ptr[i0] = p0; }
+        if (idxs[q0] == 1) { v = p1; p1 = p0; }
+        else { const int pr = prevq[q0]; v = pr >= 0 ? wrote[pr] : vals[q0]; wrote[q0] = p0; }
         p0 = v;
-        v = ptr[i1]; ptr[i1] = p1; p1 = v;
+        { const int pr = prevq[q1]; v = pr >= 0 ? wrote[pr] : vals[q1]; wrote[q1] = p1; p1 = v; }
         pairs[2 * s] = p0;
         pairs[2 * s + 1] = p1;
       }
-      ptr[0] = p0; ptr[1] = p1;
     }
     DG_SYNC();
-    // one warp per two-point hypothesis: support count over the off-plane correspondences
-    #pragma unroll 1
-    for (int s = c.wid; s < nw; s += c.nw) {
-      const int a = uN[pairs[2 * s]], b = uN[pairs[2 * s + 1]];
-      double aF[9];
-      f_from_plane_parallax(H, c.x1[a], c.y1[a], c.x2[a], c.y2[a], c.x1[b], c.y1[b], c.x2[b], c.y2[b], aF);
+    DG_PROF_END(47);
+    DG_PROF_BEGIN(48);
+    // One warp per two-point hypothesis: support count over the off-plane correspondences.  The count only matters
+    // when it EXCEEDS the best support so far (m_i) -- a few dozen of the thousands of hypotheses.  An FP32 UPPER BOUND
+    // of the count (filter32.h: a lower bound of every Sampson error on the centred single-precision tile, counted when
+    // it is below the threshold) settles the rest at a fifth of the instructions; hypotheses whose bound exceeds m_i
+    // are recounted exactly.
+    auto exact_count = [&](const double* aF) -> int {
       int cnt = 0;
 #if DG_DEVICE_PASS
       {  // two gathers + two residual chains in flight per lane
@@ -683,33 +722,116 @@ DG_ENGN unsigned blk_rFtH(const Ctx& c, Workspace& W, const unsigned char* hinl,
         if (f_resid_sampson(aF, c.x1[p], c.y1[p], c.x2[p], c.y2[p]) < th2) ++cnt;
       }
 #endif
-      cnt = warp_sum_i(cnt);
-      if (c.lane == 0) counts[s] = cnt;
+      return warp_sum_i(cnt);
+    };
+#if DG_DEVICE_PASS
+    if (c.t32) {
+      // The per-hypothesis preparation (epipole and F from the plane and two points, constants of the FP32 bound) is a
+      // few hundred dependent FP64 instructions and three levels of dependent loads: the (up to) eight hypotheses of
+      // this warp are prepared SIDE BY SIDE, one per lane, and handed to the whole warp through shuffles one at a time.
+      const unsigned full = 0xffffffffu;
+      const int myS = c.wid + c.lane * c.nw;
+      double aFl[9];
+      FFilter32 ffl;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { aFl[i] = 0.0; ffl.F[i] = 0.f; }
+      ffl.Er = 0.f; ffl.c1 = 1.f; ffl.c2 = 1.f; ffl.winv = 0.f; ffl.sym = 0;
+      if (c.lane < 8 && myS < nw) {
+        const int a = uN[pairs[2 * myS]], b = uN[pairs[2 * myS + 1]];
+        f_from_plane_parallax(H, c.x1[a], c.y1[a], c.x2[a], c.y2[a], c.x1[b], c.y1[b], c.x2[b], c.y2[b], aFl);
+        f_filter_setup(F_SAMPSON, aFl, *c.t32, th2, &ffl);
+      }
+      __syncwarp();
+      const float4* tp = reinterpret_cast<const float4*>(tileN);
+      const int npair = (nN + 1) >> 1;
+      const int last = (nN & 1) ? npair - 1 : -1;
+      #pragma unroll 1
+      for (int l = 0; l < 8; ++l) {
+        const int s = c.wid + l * c.nw;
+        if (s >= nw) break;
+        FFilter32 ff;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ff.F[i] = __shfl_sync(full, ffl.F[i], l);
+        ff.Er = __shfl_sync(full, ffl.Er, l); ff.c1 = __shfl_sync(full, ffl.c1, l);
+        ff.c2 = __shfl_sync(full, ffl.c2, l); ff.winv = __shfl_sync(full, ffl.winv, l);
+        ff.sym = 0;
+        FFilter32x2 f2;
+        f_filter_pack(ff, &f2);
+        int ub = 0;
+        int i = c.lane;
+        #pragma unroll 1
+        for (; i + 32 < npair; i += 64) {
+          const float4 A0 = tp[2 * i], B0 = tp[2 * i + 1], A1 = tp[2 * i + 64], B1 = tp[2 * i + 65];
+          float g0, g1, g2, g3;
+          upk2(f_filter_gain2(f2, A0, B0, i != last), g0, g1);
+          upk2(f_filter_gain2(f2, A1, B1, i + 32 != last), g2, g3);
+          ub += (g0 > 0.0f ? 1 : 0) + (g1 > 0.0f ? 1 : 0) + (g2 > 0.0f ? 1 : 0) + (g3 > 0.0f ? 1 : 0);
+        }
+        if (i < npair) {
+          float g0, g1;
+          upk2(f_filter_gain2(f2, tp[2 * i], tp[2 * i + 1], i != last), g0, g1);
+          ub += (g0 > 0.0f ? 1 : 0) + (g1 > 0.0f ? 1 : 0);
+        }
+        ub = warp_sum_i(ub);
+        int cnt = ub;
+        if ((unsigned)ub > m_i) {
+          double aF[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) aF[k] = shfl_d(aFl[k], l);
+          cnt = exact_count(aF);
+        }
+        if (c.lane == 0) counts[s] = cnt;
+      }
+    } else
+#endif
+    {
+      #pragma unroll 1
+      for (int s = c.wid; s < nw; s += c.nw) {
+        const int a = uN[pairs[2 * s]], b = uN[pairs[2 * s + 1]];
+        double aF[9];
+        f_from_plane_parallax(H, c.x1[a], c.y1[a], c.x2[a], c.y2[a], c.x1[b], c.y1[b], c.x2[b], c.y2[b], aF);
+        int cnt = -1;
+#if !DG_DEVICE_PASS
+        if (c.t32) {   // host emulation: the same bound, one correspondence at a time
+          FFilter32 ff;
+          f_filter_setup(F_SAMPSON, aF, *c.t32, th2, &ff);
+          int ub = 0;
+          for (int i = 0; i < nN; ++i) ub += (f_filter_gain(ff, c.t32->pts[uN[i]]) > 0.0f) ? 1 : 0;
+          if ((unsigned)ub <= m_i) cnt = ub;
+#ifdef DG_FILTER_CHECK
+          { const int ex = exact_count(aF); ++g_pp_checked; if (ub < ex) ++g_pp_violations; if (cnt >= 0) ++g_pp_settled; }
+#endif
+        }
+#endif
+        if (cnt < 0) cnt = exact_count(aF);
+        if (c.lane == 0) counts[s] = cnt;
+      }
     }
     DG_SYNC();
+    DG_PROF_END(48);
     int ev = -1;
     #pragma unroll 1
     for (int s = 0; s < nw; ++s)
       if ((unsigned)counts[s] > m_i) { ev = s; break; }
     DG_PROF_END(32);
     DG_PROF_COUNT(35, nw);
+    // commit the swaps of the iterations that count: all of them, or those up to the event
+    {
+      const int upto = (ev < 0) ? nw : ev + 1;
+      if (c.tid == 0) {
+        #pragma unroll 1
+        for (int q = 0; q < 2 * upto; ++q)
+          if (idxs[q] != 1) ptr[idxs[q]] = wrote[q];
+        ptr[0] = pairs[2 * (upto - 1)];
+        ptr[1] = pairs[2 * (upto - 1) + 1];
+      }
+      DG_SYNC();
+    }
     if (ev < 0) {
       cur.j += 2u * (uint32_t)nw;
       no_sam += (unsigned)nw;
       continue;
     }
-    // rewind the permutation to the state right after iteration `ev` (undo swaps ev+1..nw-1 in reverse)
-    DG_SYNC();
-    if (c.tid == 0) {
-      #pragma unroll 1
-      for (int s = nw - 1; s > ev; --s)
-        #pragma unroll 1
-        for (int pos = 1; pos >= 0; --pos) {
-          const int idx = idxs[2 * s + pos];
-          const int a = ptr[pos]; ptr[pos] = ptr[idx]; ptr[idx] = a;
-        }
-    }
-    DG_SYNC();
     cur.j += 2u * (uint32_t)(ev + 1);
     no_sam += (unsigned)(ev + 1);
     // event: new best two-point support -> LO from plane + parallax points

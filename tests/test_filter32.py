@@ -56,3 +56,29 @@ def test_homography_upper_bound_holds_and_results_unchanged(scale):
     E.emu_hfilter_stats(ctypes.byref(ck), ctypes.byref(vi))
     assert ck.value - c0 > 150, "filter was not exercised"
     assert vi.value - v0 == 0, "FP32 bound fell below the FP64 score %d times" % (vi.value - v0)
+
+
+@pytest.mark.parametrize("scale", [1.0, 5.0, 0.2])
+def test_plane_and_parallax_count_bound_holds_and_results_unchanged(scale):
+    """DEGENSAC's plane-and-parallax search (rFtH) counts the support of thousands of two-point hypotheses; only counts
+    above the best so far matter.  The FP32 bound must never fall below the exact count, must settle nearly all of the
+    hypotheses, and switching it off must not change a byte of the result."""
+    from tests.hostemu import emu
+    from pydegensac_b200.scenes import scene_F
+    E = emu.lib()
+    ck = ctypes.c_long(); vi = ctypes.c_long(); se = ctypes.c_long()
+    E.emu_pp_stats(ctypes.byref(ck), ctypes.byref(vi), ctypes.byref(se)); c0, v0, s0 = ck.value, vi.value, se.value
+    for sc in range(3):
+        p1, p2, _ = scene_F(1500, 0.35, 40 + sc, 0.8)
+        p1 = p1 * scale + 1000.0 * (scale - 1.0)
+        p2 = p2 * scale - 300.0 * (scale - 1.0)
+        kw = dict(px_th=1.0 * scale, conf=0.9999, max_iters=4000, seed=sc)
+        E.emu_set_filter32(1); a = emu.find_fundamental(p1, p2, **kw)
+        E.emu_set_filter32(0); b = emu.find_fundamental(p1, p2, **kw)
+        E.emu_set_filter32(1)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    E.emu_pp_stats(ctypes.byref(ck), ctypes.byref(vi), ctypes.byref(se))
+    checked, settled = ck.value - c0, se.value - s0
+    assert checked > 1000, "the plane-and-parallax search was not exercised"
+    assert vi.value - v0 == 0, "FP32 count bound fell below the exact count %d times" % (vi.value - v0)
+    assert settled > 0.9 * checked, "the bound settles too few hypotheses (%d of %d)" % (settled, checked)

@@ -35,3 +35,4 @@ print("rFtH: 2-pt hypotheses/pair %.0f  wave time %.2f Mcyc/pair   events/pair %
 print("inner_FH: dual_sample %.2f Mcyc/pair   u2Fit/pair %.2f (%.0f kcyc each, %.2f Mcyc/pair)" % (buf[36] / P / 1e6, buf[38] / P, per(37, 38) / 1e3, buf[37] / P / 1e6))
 print("big fits/pair %.1f (%.0f kcyc each, %.2f Mcyc/pair)" % (buf[39] / P, per(40, 39) / 1e3, buf[40] / P / 1e6))
 print("fused 8-pt fit: sample+replay %.1f k  gather+weights %.1f k  GJ %.1f k  rank2+store %.1f k  closing barrier %.1f k  (per call)" % tuple(buf[i] / max(buf[27], 1) / 1e3 for i in (41, 42, 43, 44, 45)))
+print("rFtH wave parts: swap replay (thread 0) %.2f Mcyc/pair   hypothesis loop %.2f Mcyc/pair" % (buf[47] / P / 1e6, buf[48] / P / 1e6))
