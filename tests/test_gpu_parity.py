@@ -300,6 +300,25 @@ def test_fp32_wave_filter_does_not_change_results(monkeypatch):
         assert np.array_equal(x, y)
 
 
+def test_plane_and_parallax_count_bound_does_not_change_results(monkeypatch):
+    """Dominant-plane scenes spend their time in DEGENSAC's plane-and-parallax search, whose two-point hypotheses are
+    settled by an FP32 upper bound of their support on a packed tile of the off-plane correspondences (odd and even
+    list lengths).  Without the filter tile (DGB200_FILTER32=0) every hypothesis is counted exactly in FP64: the outputs
+    must be byte-identical."""
+    from pydegensac_b200 import _cabi
+    for (n, frac, plane, P) in [(2000, 0.3, 0.8, 48), (701, 0.4, 0.6, 32), (300, 0.5, 0.9, 32)]:
+        b1, b2 = batch_F(P, n, frac, seed0=40, plane_frac=plane)
+        seeds = np.arange(P, dtype=np.uint64) + 40
+        monkeypatch.delenv("DGB200_FILTER32", raising=False)
+        on = _cabi.fundamental_batch(b1, b2, 1.0, 0.9999, 10000, 0, True, 0.0, True, seeds)
+        monkeypatch.setenv("DGB200_FILTER32", "0")
+        off = _cabi.fundamental_batch(b1, b2, 1.0, 0.9999, 10000, 0, True, 0.0, True, seeds)
+        monkeypatch.delenv("DGB200_FILTER32")
+        for x, y in zip(on, off):
+            assert np.array_equal(x, y)
+        assert (on[2][:, 2] > 0).sum() >= P // 4, "the plane branch was hardly exercised"   # stats[2] = plane inliers found
+
+
 def test_fp32_wave_filter_homography(monkeypatch, ref_oracle):
     """The H wave's FP32 filter (Sampson metric): byte-identical outputs with the filter on and off at N = 5000 (tile in
     the slab) and N = 1200 (tile in shared memory), odd N included (padding slot of the pair-interleaved tile)."""
