@@ -34,7 +34,88 @@ struct HParams {
   int final_lsq;    // __FINAL_LSQ__ (exp_ranH.c:16, 866-870)
 };
 
-DG_ENGN void blk_resid_H(const Ctx& c, int metric, const double* h, double* out) {
+#ifdef DG_FILTER_CHECK
+constexpr int kResidClassifyMinN = 64;     // host emulation: exercise the classification in the tests
+#else
+constexpr int kResidClassifyMinN = 2048;
+#endif
+#ifdef DG_FILTER_CHECK
+static long g_hres_points = 0, g_hres_far = 0, g_hres_violations = 0;   // residual-row classification (host emulation)
+#endif
+// Residual row of all correspondences under h.  Every consumer of a row compares its entries with thresholds of at most
+// TC MWM th = 8 th (inlier lists) and 9/4 of that (MSAC gain), i.e. an entry >= 18 th acts the same whatever its value.
+// With the Sampson metric (HDs: ~300 FP64 instructions and 8 divisions per correspondence) the row is therefore built in
+// two steps when the FP32 tile of the pair exists: (1) the FP32 LOWER bound of the error of filter32.h classifies every
+// correspondence, two per instruction; those whose bound reaches 18 th get +inf; (2) the others -- inliers and near
+// misses, a third of a typical pair -- are listed (order irrelevant) and evaluated exactly, densely packed over the
+// threads.  A bound that is not an ordinary number (NaN / overflow) sends the correspondence to the exact path.
+DG_ENGN void blk_resid_H(const Ctx& c, const HParams& P, Workspace& W, const double* h, double* out) {
+  const int metric = P.metric;
+  // (short rows: the per-row set-up and the extra barrier cost more than the classification saves -- measured at N = 811)
+  if (metric == H_SAMPSON && c.t32 && P.th > 0 && c.N >= kResidClassifyMinN) {
+    const double tmax = (kTC * kMWM * 9.0 / 4.0) * P.th;
+    HFilter32 hf;
+    h_filter_setup(h, *c.t32, tmax, &hf);
+    int* list = W.itmp[3];
+    DG_SYNC();
+    if (c.tid == 0) c.sc->counter[3] = 0;
+    DG_SYNC();
+#if DG_DEVICE_PASS
+    {
+      HFilter32x2 f2;
+      h_filter_pack(hf, &f2);
+      const float4* tp = reinterpret_cast<const float4*>(c.t32->pts);
+      const int npair = (c.N + 1) >> 1;
+      const unsigned full = 0xffffffffu, lt = (1u << c.lane) - 1u;
+      #pragma unroll 1
+      for (int qb = c.wid * 32; qb < npair; qb += c.nt) {
+        const int q = qb + c.lane;
+        const bool live0 = q < npair, live1 = (2 * q + 1) < c.N;
+        float r0 = 1.0f, r1 = 1.0f;
+        if (live0) upk2(h_filter_raw2(f2, tp[2 * q], tp[2 * q + 1]), r0, r1);
+        const bool far0 = (r0 <= 0.0f) && (r0 >= -3.0e38f), far1 = (r1 <= 0.0f) && (r1 >= -3.0e38f);
+        const bool n0 = live0 && !far0, n1 = live1 && !far1;
+        if (live0 && far0) st_row(out + 2 * q, INFINITY);
+        if (live1 && far1) st_row(out + 2 * q + 1, INFINITY);
+        const unsigned m0 = __ballot_sync(full, n0), m1 = __ballot_sync(full, n1);
+        const int tot = __popc(m0) + __popc(m1);
+        int base = 0;
+        if (c.lane == 0 && tot) base = atomicAdd(&c.sc->counter[3], tot);
+        base = __shfl_sync(full, base, 0);
+        if (n0) list[base + __popc(m0 & lt)] = 2 * q;
+        if (n1) list[base + __popc(m0) + __popc(m1 & lt)] = 2 * q + 1;
+      }
+    }
+#else
+    {
+      int cnt = 0;
+      for (int i = 0; i < c.N; ++i) {
+        const float r = h_filter_raw(hf, c.t32->pts[i]);
+        const bool far = (r <= 0.0f) && (r >= -3.0e38f);
+        if (far) out[i] = INFINITY; else list[cnt++] = i;
+#ifdef DG_FILTER_CHECK
+        ++g_hres_points;
+        if (far) { ++g_hres_far; if ((g_hres_far & 7) == 0) { const double e = h_resid_sampson(h, c.x1[i], c.y1[i], c.x2[i], c.y2[i]); if (!(e >= tmax)) ++g_hres_violations; } }   // (every 8th: keeps the CPU suite short)
+#endif
+      }
+      c.sc->counter[3] = cnt;
+    }
+#endif
+    DG_SYNC();
+    const int n = c.sc->counter[3];
+    #pragma unroll 1
+    for (int j = c.tid; j < n; j += 2 * c.nt) {   // two independent residual chains per trip
+      const int j2 = j + c.nt;
+      const bool two = j2 < n;
+      const int i = list[j], i2 = list[two ? j2 : j];
+      const double e0 = h_resid_sampson(h, c.x1[i], c.y1[i], c.x2[i], c.y2[i]);
+      const double e1 = h_resid_sampson(h, c.x1[i2], c.y1[i2], c.x2[i2], c.y2[i2]);
+      st_row(out + i, e0);
+      if (two) st_row(out + i2, e1);
+    }
+    DG_SYNC();
+    return;
+  }
   HSym s;
   if (metric != H_SAMPSON) h_sym_prepare(h, &s);
   #pragma unroll 1
@@ -99,7 +180,7 @@ DG_ENGN Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, in
   blk_fit_H(c, inl, (int)S.I, h);
   #pragma unroll 1
   for (int it = 0; it < kIlsqIters; ++it) {
-    blk_resid_H(c, P.metric, h, W.err[d]);
+    blk_resid_H(c, P, W, h, W.err[d]);
     Ss = blk_inlidxs(c, W.err[d], th, inl);
 #ifdef DG_TRACE
     fprintf(stderr, "iterH id=%d it=%d Ss.I=%u Ss.J=%.17g ths=%.17g\n", iterID, it, Ss.I, Ss.J, ths);
@@ -117,7 +198,7 @@ DG_ENGN Score lo_iter_H(const Ctx& c, const HParams& P, Workspace& W, int* e, in
     blk_fit_H(c, inl, (int)S.I, h);
     ths -= dth;
   }
-  blk_resid_H(c, P.metric, h, W.err[d]);
+  blk_resid_H(c, P, W, h, W.err[d]);
   S = blk_inlidxs(c, W.err[d], th, inl);
   if (score_less(maxS, S)) {
     maxS = S;
@@ -142,7 +223,7 @@ DG_ENGN Score lo_inner_H(const Ctx& c, const HParams& P, Workspace& W, int* e, i
   for (int rep = 0; rep < kRanRep; ++rep) {
     blk_randsubset(c, inliers, ninl, ssiz, cur);
     blk_fit_H(c, inliers + ninl - ssiz, ssiz, h);
-    blk_resid_H(c, P.metric, h, W.err[e[0]]);
+    blk_resid_H(c, P, W, h, W.err[e[0]]);
     e[4] = e[0];
     ++iterID;
     S = lo_iter_H(c, P, W, e, W.intbuff, th, kTC * th, h, iterID, ht);
@@ -173,7 +254,7 @@ DG_ENGN bool run_lo_H(const Ctx& c, const HParams& P, Workspace& W, HState& st, 
   const int d = st.e[0];
   Score S = blk_inlidxs(c, W.err[st.e[4]], kTC * P.th * kMWM, W.inliers);
   blk_fit_H(c, W.inliers, (int)S.I, h);
-  blk_resid_H(c, P.metric, h, W.err[d]);
+  blk_resid_H(c, P, W, h, W.err[d]);
   S = blk_inlidxs(c, W.err[d], P.th, W.inliers);
 #ifdef DG_TRACE_DEV
   if (c.tid == 0) printf("LOH start ninl=%u J=%.12g\n", S.I, S.J);
@@ -338,7 +419,7 @@ DG_ENGN void replay_iteration_H(const Ctx& c, const HParams& P, Workspace& W, HS
   st.cur.seed = P.seed; st.cur.k = (uint32_t)k; st.cur.j = 5;
   bool new_max = false, do_iterate;
   const int d = st.e[0];
-  blk_resid_H(c, P.metric, h, W.err[d]);
+  blk_resid_H(c, P, W, h, W.err[d]);
   Score S = blk_inlidxs(c, W.err[d], P.th, W.itmp[0]);
 #ifdef DG_TRACE_DEV
   if (c.tid == 0) printf("RH k=%d S.I=%u S.J=%.12g maxS.J=%.12g maxSs.J=%.12g iter=%d\n", k, S.I, S.J, st.maxS.J, st.maxSs.J, st.iter_cnt);
@@ -441,7 +522,7 @@ DG_ENGN void ransac_H_pair(const Ctx& c, const HParams& P, Workspace& W, double*
   if (P.final_lsq) {   // exp_ranH.c:866-870: LSQ on all inliers of the best model, residuals (and the mask) from it
     const Score Sl = blk_inlidxs(c, d, P.th, W.inliers);
     blk_fit_H(c, W.inliers, (int)Sl.I, st.H);
-    blk_resid_H(c, P.metric, st.H, d);
+    blk_resid_H(c, P, W, st.H, d);
   }
   #pragma unroll 1
   for (int j = c.tid; j < c.N; j += c.nt) mask_out[j] = (d[j] <= P.th) ? 1 : 0;

@@ -250,7 +250,8 @@ DG_HD void h_filter_setup(const double* h, const Tile32& T, double w, HFilter32*
   o->c2 = (float)(Eg * Eg * 4097.0 * 1.0001);
   o->winv = (float)((1.0 / w) * (1.0 - 7.62939453125e-06) * (1.0 - 1e-6));
 }
-DG_HD float h_filter_gain(const HFilter32& f, const Pt32& p) {
+// 1 - e_lo / w WITHOUT the clamp at zero (h_filter_gain clamps): <= 0 means "the Sampson error is at least w".
+DG_HD float h_filter_raw(const HFilter32& f, const Pt32& p) {
 #if DG_DEVICE_PASS
 #define DG_FMAF __fmaf_rn
 #define DG_RCPF(x) __fdividef(1.0f, (x))
@@ -275,7 +276,10 @@ DG_HD float h_filter_gain(const HFilter32& f, const Pt32& p) {
 #undef DG_FMAF
 #undef DG_RCPF
 #undef DG_SQRTF
-  const float g = 1.0f - e_lo * f.winv;
+  return 1.0f - e_lo * f.winv;
+}
+DG_HD float h_filter_gain(const HFilter32& f, const Pt32& p) {
+  const float g = h_filter_raw(f, p);
   return g > 0.0f ? g : 0.0f;
 }
 
@@ -293,7 +297,7 @@ __device__ __forceinline__ void h_filter_pack(const HFilter32& f, HFilter32x2* o
   o->half = pk2(0.5f, 0.5f); o->mone = pk2(-1.0f, -1.0f);
   o->Er = f.Er;
 }
-__device__ __forceinline__ f32x2 h_filter_gain2(const HFilter32x2& f, const float4 A4, const float4 B4, bool hi_live) {
+__device__ __forceinline__ f32x2 h_filter_raw2(const HFilter32x2& f, const float4 A4, const float4 B4) {
   const f32x2 u = pk2(A4.x, A4.y), v = pk2(A4.z, A4.w), s = pk2(B4.x, B4.y), t = pk2(B4.z, B4.w);
   const f32x2 nw = fma2(f.nH2, s, fma2(f.nH5, t, f.nH8));
   const f32x2 r1 = fma2(u, nw, fma2(f.H0, s, fma2(f.H3, t, f.H6)));
@@ -314,8 +318,11 @@ __device__ __forceinline__ f32x2 h_filter_gain2(const HFilter32x2& f, const floa
   float d0, d1;
   upk2(fma2(lam, f.c1, f.c2), d0, d1);
   const f32x2 el = mul2(fma2(l1, l1, mul2(l2, l2)), pk2(__fdividef(1.0f, d0), __fdividef(1.0f, d1)));
+  return fma2(el, f.nwinv, f.one);
+}
+__device__ __forceinline__ f32x2 h_filter_gain2(const HFilter32x2& f, const float4 A4, const float4 B4, bool hi_live) {
   float g0, g1;
-  upk2(fma2(el, f.nwinv, f.one), g0, g1);
+  upk2(h_filter_raw2(f, A4, B4), g0, g1);
   g0 = fmaxf(g0, 0.0f);
   g1 = hi_live ? fmaxf(g1, 0.0f) : 0.0f;
   return pk2(g0, g1);

@@ -17,6 +17,7 @@ using namespace dg;
 static int g_use_filter32 = 1;
 extern "C" void emu_set_filter32(int on) { g_use_filter32 = on; }
 extern "C" void emu_hfilter_stats(long* checked, long* violations) { *checked = g_hfilter_checked; *violations = g_hfilter_violations; }
+extern "C" void emu_hres_stats(long* points, long* far, long* violations) { *points = g_hres_points; *far = g_hres_far; *violations = g_hres_violations; }
 extern "C" void emu_pp_stats(long* checked, long* violations, long* settled) { *checked = g_pp_checked; *violations = g_pp_violations; *settled = g_pp_settled; }
 extern "C" void emu_filter_stats(long* checked, long* violations, double* maxslack) {
   *checked = g_filter_checked; *violations = g_filter_violations; *maxslack = g_filter_maxslack;

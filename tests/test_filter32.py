@@ -82,3 +82,27 @@ def test_plane_and_parallax_count_bound_holds_and_results_unchanged(scale):
     assert checked > 1000, "the plane-and-parallax search was not exercised"
     assert vi.value - v0 == 0, "FP32 count bound fell below the exact count %d times" % (vi.value - v0)
     assert settled > 0.9 * checked, "the bound settles too few hypotheses (%d of %d)" % (settled, checked)
+
+
+def test_homography_residual_row_classification_is_safe():
+    """The H driver builds its residual rows in two steps (Sampson metric): an FP32 lower bound of the error marks the
+    correspondences that are at least 18 th away (they get +inf: no consumer of a row looks beyond 18 th), the rest is
+    evaluated exactly.  Every correspondence marked 'far' must really be that far, and most outliers must be caught."""
+    from tests.hostemu import emu
+    from pydegensac_b200.scenes import scene_H
+    E = emu.lib()
+    pt = ctypes.c_long(); fa = ctypes.c_long(); vi = ctypes.c_long()
+    E.emu_hres_stats(ctypes.byref(pt), ctypes.byref(fa), ctypes.byref(vi)); p0, f0, v0 = pt.value, fa.value, vi.value
+    for sc, scale in enumerate((1.0, 7.0, 0.15)):
+        p1, p2, _ = scene_H(1500, 300 + 100 * sc, 90 + sc)
+        p1 = p1 * scale + 3000.0 * (scale - 1.0)
+        p2 = p2 * scale - 800.0 * (scale - 1.0)
+        kw = dict(px_th=3.0 * scale, conf=0.999, max_iters=3000, seed=sc)
+        E.emu_set_filter32(1); a = emu.find_homography_raw(p1, p2, **kw)
+        E.emu_set_filter32(0); b = emu.find_homography_raw(p1, p2, **kw)
+        E.emu_set_filter32(1)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    E.emu_hres_stats(ctypes.byref(pt), ctypes.byref(fa), ctypes.byref(vi))
+    assert pt.value - p0 > 100000, "the classification was not exercised"
+    assert vi.value - v0 == 0, "a correspondence marked far was closer than 18 th (%d times)" % (vi.value - v0)
+    assert fa.value - f0 > 0.5 * (pt.value - p0)
