@@ -150,21 +150,53 @@ static void left_null(double *Z, int len, double *q) {
   memset(q, 0, 9 * sizeof(double)); q[8] = 1;
   for (int c = len - 1; c >= 0; --c) { double d = 0; for (int r = c; r < 9; ++r) d += vs[c][r] * q[r]; d *= beta[c]; for (int r = c; r < 9; ++r) q[r] -= d * vs[c][r]; }
 }
-/* 3x3 inverse with the singularity rule of CCMATH minv (matutls/minv.c:11,27) */
+/* 3x3 inverse with the arithmetic of CCMATH minv, operation for operation (matutls/minv.c:10-71): column-wise Crout LU
+ * with row pivoting, both factors inverted in place, product, interchanges undone on the columns.  Bit-for-bit equal to
+ * the reference's (tests/test_small_la.py); the symmetric-transfer metrics need that on scenes where exact four-point fits
+ * compete with scores that differ by rounding noise only. */
 static int inv3(double *a) {
-  double m[3][6], tq = 0;
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { m[i][j] = a[3 * i + j]; m[i][3 + j] = i == j; }
-  for (int c = 0; c < 3; ++c) {
-    int best = c; double s = fabs(m[c][c]);
-    for (int r = c + 1; r < 3; ++r) if (fabs(m[r][c]) > s) { s = fabs(m[r][c]); best = r; }
-    if (s > tq) tq = s;
-    if (s < 1e-15 * tq || s == 0) return -1;
-    for (int k = 0; k < 6; ++k) { double t = m[c][k]; m[c][k] = m[best][k]; m[best][k] = t; }
-    double inv = 1 / m[c][c];
-    for (int k = 0; k < 6; ++k) m[c][k] *= inv;
-    for (int r = 0; r < 3; ++r) if (r != c) { double f = m[r][c]; for (int k = 0; k < 6; ++k) m[r][k] -= f * m[c][k]; }
+  enum { n = 3 };
+  int le[n]; double q0[n], tq = 0, zr = 1.e-15;
+  for (int j = 0; j < n; ++j) {
+    if (j > 0) {
+      for (int i = 0; i < n; ++i) q0[i] = a[i * n + j];
+      for (int i = 1; i < n; ++i) { int lc = i < j ? i : j; double t = 0; for (int k = 0; k < lc; ++k) t += a[i * n + k] * q0[k]; q0[i] -= t; }
+      for (int i = 0; i < n; ++i) a[i * n + j] = q0[i];
+    }
+    double s = fabs(a[j * n + j]); int lc = j;
+    for (int k = j + 1; k < n; ++k) { double t = fabs(a[k * n + j]); if (t > s) { s = t; lc = k; } }
+    tq = tq > s ? tq : s;
+    if (s < zr * tq) return -1;
+    le[j] = lc;
+    if (lc != j) for (int k = 0; k < n; ++k) { double t = a[j * n + k]; a[j * n + k] = a[lc * n + k]; a[lc * n + k] = t; }
+    double t = 1. / a[j * n + j];
+    for (int k = j + 1; k < n; ++k) a[k * n + j] *= t;
+    a[j * n + j] = t;
   }
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) a[3 * i + j] = m[i][3 + j];
+  for (int j = 1; j < n; ++j) for (int k = 0; k < j; ++k) a[k * n + j] *= a[j * n + j];
+  for (int j = 1; j < n; ++j) {
+    for (int i = 0; i < j; ++i) q0[i] = a[i * n + j];
+    for (int k = 0; k < j; ++k) { double t = 0; for (int i = k; i < j; ++i) t -= a[k * n + i] * q0[i]; q0[k] = t; }
+    for (int i = 0; i < j; ++i) a[i * n + j] = q0[i];
+  }
+  for (int j = n - 2; j >= 0; --j) {
+    int m = n - j - 1;
+    for (int i = 0; i < m; ++i) q0[i] = a[(j + 1 + i) * n + j];
+    for (int k = n - 1; k > j; --k) { double t = -a[k * n + j]; for (int i = j + 1; i < k; ++i) t -= a[k * n + i] * q0[i - j - 1]; q0[--m] = t; }
+    m = n - j - 1;
+    for (int i = 0; i < m; ++i) a[(j + 1 + i) * n + j] = q0[i];
+  }
+  for (int k = 0; k < n - 1; ++k) {
+    for (int i = 0; i < n; ++i) q0[i] = a[i * n + k];
+    for (int j = 0; j < n; ++j) {
+      double t; int i;
+      if (j > k) { t = 0; i = j; } else { t = q0[j]; i = k + 1; }
+      for (; i < n; ++i) t += a[j * n + i] * q0[i];
+      q0[j] = t;
+    }
+    for (int i = 0; i < n; ++i) a[i * n + k] = q0[i];
+  }
+  for (int j = n - 2; j >= 0; --j) { int lc = le[j]; for (int k = 0; k < n; ++k) { double t = a[k * n + j]; a[k * n + j] = a[k * n + lc]; a[k * n + lc] = t; } }
   return 0;
 }
 static void cross(double *o, const double *a, const double *b) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; }

@@ -278,3 +278,7 @@ int ref_h_from_2el(const double *ua, const double *ub, double *h) {
   getTransf(u, N1, D1); getTransf(u + 10, N2, D2);
   return A2toRH(N1, D1, N2, D2, u, samidx, h) ? 0 : 1;
 }
+
+/* CCMATH minv (matutls/minv.c) exposed for the bit-for-bit test of the engine's restatement. */
+extern int minv(double *a, int n);
+int ref_minv3(double *a) { return minv(a, 3); }

@@ -60,7 +60,7 @@ DG_HDN void h_from_F_3pts(const double* F, const double* u7, const int* tri, dou
     b[t] = (p1[0] * p2[0] + p1[1] * p2[1] + p1[2] * p2[2]) / (p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
     M[3 * t] = a2[0]; M[3 * t + 1] = a2[1]; M[3 * t + 2] = a2[2];
   }
-  const int sing = inv3(M);
+  const int sing = minv3(M);   // CCMATH minv, bit for bit (DegUtils.c:141)
   double v[3];
   for (int i = 0; i < 3; ++i) v[i] = M[3 * i] * b[0] + M[3 * i + 1] * b[1] + M[3 * i + 2] * b[2];
   for (int i = 0; i < 3; ++i)

@@ -109,7 +109,7 @@ DG_HDN void h_sym_prepare(const double* H, HSym* s) {
   s->Hi[3] = H[1]; s->Hi[4] = H[4]; s->Hi[5] = H[7];
   s->Hi[6] = H[2]; s->Hi[7] = H[5]; s->Hi[8] = H[8];
   for (int i = 0; i < 9; ++i) s->H1[i] = s->Hi[i];
-  inv3(s->H1);
+  minv3(s->H1);   // the reference's own inverse, bit for bit (la.h)
 }
 // d1 = |x2 - H1 x1|^2, d2 = |x1 - Hi x2|^2 ; eps is the 1e-10 the reference adds to some denominators.
 DG_HD void h_sym_d1d2(const HSym& s, double x1, double y1, double x2, double y2, double eps, double* d1, double* d2) {

@@ -636,6 +636,108 @@ DG_HDN int inv3(double* a) {
   return 0;
 }
 
+// In-place inverse of a 3x3 row-major matrix with EXACTLY the arithmetic of CCMATH's minv (matutls/minv.c:10-71):
+// column-wise Crout LU with row pivoting (pivot compared with 1e-15 x the largest pivot so far), the two triangular
+// factors inverted in place, multiplied, and the row interchanges undone as column interchanges.  Needed bit for bit:
+// the symmetric-transfer metrics of the H driver push every correspondence through this inverse, and on scenes whose
+// best sample is supported by nothing but its own four points the MSAC scores 4 - O(1e-13) of two exact fits differ
+// only by the rounding noise of this routine -- which decides whether the reference schedules one more LO.  Returns -1
+// on a vanishing pivot, with the matrix left half-processed exactly as the reference leaves it (its callers ignore the
+// return value).
+DG_HDN int minv3(double* a) {
+  const int n = 3;
+  int le[3];
+  double q0[3];
+  double tq = 0.0;
+  const double zr = 1.e-15;
+  #pragma unroll 1
+  for (int j = 0; j < n; ++j) {
+    if (j > 0) {
+      for (int i = 0; i < n; ++i) q0[i] = a[i * n + j];
+      #pragma unroll 1
+      for (int i = 1; i < n; ++i) {
+        const int lc = i < j ? i : j;
+        double t = 0.0;
+        #pragma unroll 1
+        for (int k = 0; k < lc; ++k) t += a[i * n + k] * q0[k];
+        q0[i] -= t;
+      }
+      for (int i = 0; i < n; ++i) a[i * n + j] = q0[i];
+    }
+    double s = fabs(a[j * n + j]);
+    int lc = j;
+    #pragma unroll 1
+    for (int k = j + 1; k < n; ++k) {
+      const double t = fabs(a[k * n + j]);
+      if (t > s) { s = t; lc = k; }
+    }
+    tq = tq > s ? tq : s;
+    if (s < zr * tq) return -1;
+    le[j] = lc;
+    if (lc != j) {
+      for (int k = 0; k < n; ++k) { const double t = a[j * n + k]; a[j * n + k] = a[lc * n + k]; a[lc * n + k] = t; }
+    }
+    const double t = 1. / a[j * n + j];
+    #pragma unroll 1
+    for (int k = j + 1; k < n; ++k) a[k * n + j] *= t;
+    a[j * n + j] = t;
+  }
+  #pragma unroll 1
+  for (int j = 1; j < n; ++j)
+    #pragma unroll 1
+    for (int k = 0; k < j; ++k) a[k * n + j] *= a[j * n + j];
+  #pragma unroll 1
+  for (int j = 1; j < n; ++j) {
+    #pragma unroll 1
+    for (int i = 0; i < j; ++i) q0[i] = a[i * n + j];
+    #pragma unroll 1
+    for (int k = 0; k < j; ++k) {
+      double t = 0.0;
+      #pragma unroll 1
+      for (int i = k; i < j; ++i) t -= a[k * n + i] * q0[i];
+      q0[k] = t;
+    }
+    #pragma unroll 1
+    for (int i = 0; i < j; ++i) a[i * n + j] = q0[i];
+  }
+  #pragma unroll 1
+  for (int j = n - 2; j >= 0; --j) {
+    int m = n - j - 1;
+    #pragma unroll 1
+    for (int i = 0; i < m; ++i) q0[i] = a[(j + 1 + i) * n + j];
+    #pragma unroll 1
+    for (int k = n - 1; k > j; --k) {
+      double t = -a[k * n + j];
+      #pragma unroll 1
+      for (int i = j + 1; i < k; ++i) t -= a[k * n + i] * q0[i - j - 1];
+      q0[--m] = t;
+    }
+    m = n - j - 1;
+    #pragma unroll 1
+    for (int i = 0; i < m; ++i) a[(j + 1 + i) * n + j] = q0[i];
+  }
+  #pragma unroll 1
+  for (int k = 0; k < n - 1; ++k) {
+    for (int i = 0; i < n; ++i) q0[i] = a[i * n + k];
+    #pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+      double t;
+      int i;
+      if (j > k) { t = 0.0; i = j; } else { t = q0[j]; i = k + 1; }
+      #pragma unroll 1
+      for (; i < n; ++i) t += a[j * n + i] * q0[i];
+      q0[j] = t;
+    }
+    for (int i = 0; i < n; ++i) a[i * n + k] = q0[i];
+  }
+  #pragma unroll 1
+  for (int j = n - 2; j >= 0; --j) {
+    const int lc = le[j];
+    for (int k = 0; k < n; ++k) { const double t = a[k * n + j]; a[k * n + j] = a[k * n + lc]; a[k * n + lc] = t; }
+  }
+  return 0;
+}
+
 DG_HD double det3(const double* A) {  // utools.c:196-202
   double r = (A[0] * A[4] * A[8] + A[2] * A[3] * A[7] + A[1] * A[5] * A[6]);
   r -= (A[2] * A[4] * A[6] + A[0] * A[5] * A[7] + A[1] * A[3] * A[8]);

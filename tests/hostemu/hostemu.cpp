@@ -115,6 +115,7 @@ extern "C" long emu_u2h4_calls(int reset) { const long v = g_u2h4_calls; if (res
 extern "C" int emu_h_from_2el(const double* ua, const double* ub, double* h) { return h_from_2el(ua, ub, h) ? 1 : 0; }
 
 // ---- leaf exports for known-answer tests against the reference's own leaves ----
+extern "C" int emu_minv3(double* a) { return minv3(a); }
 extern "C" int emu_nullspace9(double* M, double* ns) { return nullspace9(M, ns); }
 extern "C" void emu_seven_pt_cubic(const double* A, double* B, double* p) { seven_pt_cubic(A, B, p); }
 extern "C" int emu_cubic_real_roots(const double* po, double* r) { return cubic_real_roots(po, r); }
