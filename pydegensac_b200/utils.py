@@ -154,6 +154,16 @@ def findFundamentalMatrix(pts1_,
     return F, mask
 
 
+def _opencv_convention(Hraw):
+    """[P,3,3] raw core outputs (column-major, image 2 -> image 1) -> inv(H^T) per pair as utils.py:108 of the reference
+    does for one; a zero model (nothing found) stays zero.  One batched LAPACK call instead of P Python-level ones."""
+    H = np.zeros_like(Hraw)
+    found = np.abs(Hraw).reshape(Hraw.shape[0], -1).sum(axis=1) != 0
+    if found.any():
+        H[found] = np.linalg.inv(np.transpose(Hraw[found], (0, 2, 1)))
+    return H
+
+
 def _batch_seeds(seeds, P):
     if seeds is None:
         base = _seed_value(None)
@@ -222,19 +232,13 @@ def findHomographyBatch(pts1, pts2, px_th=1.0, conf=0.999, max_iters=50000, erro
         Hraw, masks, stats = _cabi.homography_ragged(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check,
                                                      _batch_laf(laf_consistensy_coef, np.asarray(pts1[0])),
                                                      _batch_seeds(seeds, len(pts1)))
-        H = np.zeros_like(Hraw)
-        for i in range(Hraw.shape[0]):
-            if np.abs(Hraw[i]).sum() != 0:
-                H[i] = np.linalg.inv(Hraw[i].T)
+        H = _opencv_convention(Hraw)
         return (H, masks, stats) if return_stats else (H, masks)
     p1 = np.asarray(pts1)
     Hraw, mask, stats = _cabi.homography_batch(pts1, pts2, px_th, conf, max_iters, et, symmetric_error_check,
                                                _batch_laf(laf_consistensy_coef, p1), _batch_seeds(seeds, p1.shape[0]),
                                                flags=_cabi.FLAG_FINAL_LSQ if final_lsq else 0)
-    H = np.zeros_like(Hraw)
-    for i in range(Hraw.shape[0]):
-        if np.abs(Hraw[i]).sum() != 0:
-            H[i] = np.linalg.inv(Hraw[i].T)
+    H = _opencv_convention(Hraw)
     return (H, mask, stats) if return_stats else (H, mask)
 
 
@@ -275,10 +279,7 @@ def findHomographyFromEllipses(frames1, frames2, px_th=1.0, conf=0.999, max_iter
         seeds = np.full(P, _seed_value(seed), dtype=np.uint64) if single else _batch_seeds(None, P)
     u10 = np.concatenate([f1, f2], axis=2)
     Hraw, mask, stats = _cabi.homography_2el_batch(u10, px_th, conf, max_iters, seeds)
-    H = np.zeros_like(Hraw)
-    for i in range(P):
-        if np.abs(Hraw[i]).sum() != 0:
-            H[i] = np.linalg.inv(Hraw[i].T)
+    H = _opencv_convention(Hraw)
     if single:
         H, mask, stats = H[0], mask[0], stats[0]
     return (H, mask, stats) if return_stats else (H, mask)
